@@ -1,0 +1,115 @@
+/*
+ * sesa_b200 — C ABI of the B200-native chunked-separation hot path.
+ *
+ * Drop-in boundary for the path behind SESA's demix() (reference: /root/reference/utils.py:330-477,
+ * inference_pytorch.py:55-186) and the BS-RoFormer / Mel-Band-RoFormer / MDX23C forward passes
+ * (models/bs_roformer/bs_roformer.py:447-587, models/bs_roformer/mel_band_roformer.py:480-633,
+ * models/mdx23c_tfc_tdf_v3.py:205-242).  The reference is pure Python on top of PyTorch library
+ * kernels, so each entry point replaces a LIBRARY CALL SITE of the reference (cited per function);
+ * the Python host in sesa_audio_separation_b200/ mirrors the reference's operator surface and binds
+ * these symbols with ctypes.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless its name ends in _host; sizes are elements;
+ * `stream` is a cudaStream_t passed as void*; nothing is allocated, freed or synchronised by the
+ * library; every function returns 0 on success or a SESA_ERR_* code, with a message retrievable
+ * from sesa_last_error().  There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with SESA_ERR_CUDA.
+ */
+#ifndef SESA_B200_H
+#define SESA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SESA_B200_ABI_VERSION 1
+
+enum { SESA_ACT_NONE = 0, SESA_ACT_GELU = 1, SESA_ACT_TANH = 2, SESA_ACT_SIGMOID = 3 };
+
+/* One problem of a grouped GEMM  C[M,N] = epi(A[M,K] . W[N,K]^T)  (W in nn.Linear layout). */
+typedef struct sesa_gemm_group {
+  const float* A;
+  const float* W;
+  const float* bias; /* [N] or NULL */
+  float* C;
+  int32_t M, N, K, _pad;
+  int64_t lda, ldw, ldc;
+} sesa_gemm_group;
+
+/* Epilogue shared by all groups of a launch. */
+typedef struct sesa_gemm_epilogue {
+  int32_t rownorm;  /* scale row m by 1/max(||A[m,:]||_2, 1e-12): fused RMSNorm (bs_roformer.py:43-50),
+                       gamma*sqrt(K) being folded into W by the host */
+  int32_t act;      /* SESA_ACT_*: GELU(erf) bs_roformer.py:66, tanh :271, sigmoid */
+  int32_t residual; /* C += result (bs_roformer.py:214-215) */
+  int32_t glu;      /* nn.GLU (bs_roformer.py:296): W rows interleaved (value,gate); writes N/2 columns */
+  int32_t rot_cols; /* rotary embedding on column pairs n < rot_cols (bs_roformer.py:112-113) */
+  int32_t rot_dim;  /* head dim */
+  int32_t pos_div, pos_mod; /* sequence position of row m = (m / pos_div) % pos_mod */
+  const float* rot; /* [pos_mod][rot_dim/2][2] = (cos, sin) */
+} sesa_gemm_epilogue;
+
+int sesa_abi_version(void);
+const char* sesa_last_error(void);
+/* 0 and *sm_count etc filled when a CUDA device is usable. */
+int sesa_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem);
+
+/* ---- framing -------------------------------------------------------------------------------- */
+/* dst[c][i] = src[c][reflect(i-left)], i in [0, len+left+right): the border reflect pad of
+ * utils.py:391-393 (nn.functional.pad(mix, (border, border), mode="reflect")). */
+int sesa_pad_reflect(const float* src, float* dst, int channels, int64_t len, int64_t left, int64_t right,
+                     void* stream);
+/* chunks[k][c][0..L) = mix[c][start_k .. start_k+len_k) right-padded to L by reflection (mode 1) or zeros
+ * (mode 0): utils.py:413-425.  starts/lens/modes are device arrays of n_chunks entries. */
+int sesa_frame_chunks(const float* mix, int64_t mix_len, int channels, const int64_t* starts,
+                      const int64_t* lens, const int32_t* modes, int n_chunks, int64_t chunk_size,
+                      float* chunks, void* stream);
+
+/* ---- STFT / iSTFT --------------------------------------------------------------------------- */
+/* torch.stft(center=True, pad_mode='reflect', onesided) of n_signals groups of `channels` signals
+ * (bs_roformer.py:485, mel_band_roformer.py:516, mdx23c_tfc_tdf_v3.py:19-26).
+ * layout 0: spec[(sig*T+t)][f][c][re,im]; layout 1: spec[sig][c][re,im][f<dim_f][t].
+ * window: [n_fft]; twiddle: [n_fft][2] = exp(-2 pi i k / n_fft). */
+int sesa_stft(const float* audio, float* spec, const float* window, const float* twiddle, int n_signals,
+              int channels, int64_t length, int n_fft, int hop, int layout, int dim_f, void* stream);
+/* complex mask multiply (bs_roformer.py:556-567; Mel scatter-average mel_band_roformer.py:603-616) fused with
+ * torch.istft (bs_roformer.py:575): irFFT, window, overlap-add over frames, / window envelope, trim.
+ * mode 0: mask[n][b*T+t][f][c][2]; mode 1: mask[n][b*T+t][J][2] + inv_index[(f*C+c)*2+{0,1}], inv_count[f*C+c];
+ * mode 2: no mask, spec[(b*nstems+n)][t][f][c][2].  out[b][n][c][out_len]; envelope[out_len]. */
+int sesa_mask_istft(const float* spec, const float* mask, const int32_t* inv_index, const float* inv_count,
+                    float* out, const float* window, const float* envelope, const float* twiddle, int batch,
+                    int nstems, int channels, int n_fft, int hop, int n_frames, int64_t out_len, int mode,
+                    int n_gathered, void* stream);
+
+/* ---- dense math ----------------------------------------------------------------------------- */
+/* Exact-fp32 grouped GEMM (nn.Linear call sites bs_roformer.py:63,67,99,101,104,237,264). */
+int sesa_gemm_simt(const sesa_gemm_group* groups_dev, int n_groups, int max_m, int max_n,
+                   const sesa_gemm_epilogue* ep_host, void* stream);
+/* softmax(q k^T) v, sigmoid gating, head merge (attend.py:89-93,113-126; bs_roformer.py:115-120).
+ * Sequence s covers rows base(s) + p*pos_stride, base(s) = (s / inner_cnt)*outer_stride + (s % inner_cnt)*inner_stride.
+ * qkv row: [q | k | v | gate logits], ld floats; out row: [h d], ldo floats. */
+int sesa_attention_simt(const float* qkv, float* out, int ld, int ldo, int heads, int dim_head, int n_seq,
+                        int seq_len, int inner_cnt, int64_t outer_stride, int64_t inner_stride,
+                        int64_t pos_stride, void* stream);
+/* y[r,:] = x[r,:]/max(||x[r,:]||,1e-12) * sqrt(dim) * gamma   (RMSNorm, bs_roformer.py:43-50). In place ok. */
+int sesa_rmsnorm(const float* x, const float* gamma, float* y, int64_t rows, int dim, void* stream);
+/* y += x (skip connections, bs_roformer.py:521-524) */
+int sesa_add_inplace(float* y, const float* x, int64_t n, void* stream);
+/* out[r][j][0..w) = in[r][idx[j]][0..w)  (Mel band gather, mel_band_roformer.py:530); w floats per entry */
+int sesa_gather_rows(const float* in, const int32_t* idx, float* out, int64_t rows, int n_in, int n_out,
+                     int width, void* stream);
+
+/* ---- windowed overlap-add of chunk outputs (utils.py:432-464) ------------------------------- */
+/* chunk_out[k][n][c][L]; result[n][c][out_len] = sum_k (ascending) y*w / sum_k w over padded positions
+ * p = crop + i, NaN -> 0.  window[L] is _getWindowingArray (utils.py:295-327); kinds[k]: 0 both ramps,
+ * 1 no fade-in, 2 no fade-out (utils.py:432-437).  counter (optional, [padded_len]) receives sum_k w. */
+int sesa_overlap_add(const float* chunk_out, const int64_t* starts, const int64_t* lens, const int32_t* kinds,
+                     int n_chunks, int64_t step, int64_t chunk_size, int fade, const float* window,
+                     int nstems, int channels, int64_t padded_len, int64_t crop, int64_t out_len,
+                     float* result, float* counter, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SESA_B200_H */

@@ -1,0 +1,93 @@
+"""ctypes binding of the C-ABI in include/sesa_b200.h.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is NO
+fallback: a missing library or a missing CUDA device raises immediately.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsesa_b200.so')
+
+ACT_NONE, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+
+
+class SesaError(RuntimeError):
+    pass
+
+
+class GemmEpilogue(ctypes.Structure):
+    _fields_ = [('rownorm', c_int32), ('act', c_int32), ('residual', c_int32), ('glu', c_int32),
+                ('rot_cols', c_int32), ('rot_dim', c_int32), ('pos_div', c_int32), ('pos_mod', c_int32),
+                ('rot', c_void_p)]
+
+
+# numpy mirror of struct sesa_gemm_group (64 bytes)
+GEMM_GROUP_DTYPE = np.dtype([('A', '<u8'), ('W', '<u8'), ('bias', '<u8'), ('C', '<u8'),
+                             ('M', '<i4'), ('N', '<i4'), ('K', '<i4'), ('_pad', '<i4'),
+                             ('lda', '<i8'), ('ldw', '<i8'), ('ldc', '<i8')])
+assert GEMM_GROUP_DTYPE.itemsize == 72
+
+_SIGS = {
+    'sesa_abi_version': (c_int, []),
+    'sesa_last_error': (c_char_p, []),
+    'sesa_device_info': (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
+    'sesa_pad_reflect': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p]),
+    'sesa_frame_chunks': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+                                  c_void_p, c_void_p]),
+    'sesa_stft': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int,
+                          c_int, c_void_p]),
+    'sesa_mask_istft': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
+    'sesa_gemm_simt': (c_int, [c_void_p, c_int, c_int, c_int, POINTER(GemmEpilogue), c_void_p]),
+    'sesa_attention_simt': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_int64, c_int64, c_int64, c_void_p]),
+    'sesa_rmsnorm': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'sesa_add_inplace': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    'sesa_gather_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    'sesa_overlap_add': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int,
+                                 c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                 c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+_lib = None
+
+
+def load():
+    """Load libsesa_b200.so and bind every symbol of include/sesa_b200.h (raises if absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SesaError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                        'at the repo root (nvcc, sm_100a). There is no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sesa_abi_version() != 1:
+        raise SesaError('libsesa_b200.so ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().sesa_last_error()
+        raise SesaError(f'sesa_b200 error {status}: {msg.decode() if msg else "?"}')
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise SesaError('sesa_audio_separation_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists')
+    load()

@@ -1,0 +1,202 @@
+// Framing, overlap-add and small elementwise kernels of the demix() loop.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+#include "sesa_b200.h"
+
+static thread_local char g_err[512] = "";
+
+void sesa_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* sesa_last_error(void) { return g_err; }
+extern "C" int sesa_abi_version(void) { return SESA_B200_ABI_VERSION; }
+
+extern "C" int sesa_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem) {
+  int dev = 0;
+  SESA_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  SESA_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (total_mem) *total_mem = (int64_t)p.totalGlobalMem;
+  return SESA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void pad_reflect_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t len,
+                                   int64_t left, int64_t total) {
+  const int c = blockIdx.y;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    dst[c * total + i] = src[c * len + reflect_index(i - left, len)];
+}
+
+extern "C" int sesa_pad_reflect(const float* src, float* dst, int channels, int64_t len, int64_t left,
+                                int64_t right, void* stream) {
+  SESA_CHECK_ARG(left < len && right < len, "sesa_pad_reflect: pad (%lld,%lld) must be < len %lld",
+                 (long long)left, (long long)right, (long long)len);
+  const int64_t total = len + left + right;
+  dim3 grid((unsigned)min((int64_t)4096, ceil_div64(total, 256)), channels);
+  pad_reflect_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, len, left, total);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+__global__ void frame_chunks_kernel(const float* __restrict__ mix, int64_t mix_len, int channels,
+                                    const int64_t* __restrict__ starts, const int64_t* __restrict__ lens,
+                                    const int32_t* __restrict__ modes, int64_t L, float* __restrict__ chunks) {
+  const int k = blockIdx.z, c = blockIdx.y;
+  const int64_t s = starts[k], n = lens[k];
+  const int mode = modes[k];
+  const float* src = mix + c * mix_len + s;
+  float* dst = chunks + ((int64_t)k * channels + c) * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < n) v = src[i];
+    else if (mode == 1) v = src[2 * (n - 1) - i];
+    dst[i] = v;
+  }
+}
+
+extern "C" int sesa_frame_chunks(const float* mix, int64_t mix_len, int channels, const int64_t* starts,
+                                 const int64_t* lens, const int32_t* modes, int n_chunks, int64_t chunk_size,
+                                 float* chunks, void* stream) {
+  if (n_chunks == 0) return SESA_OK;
+  SESA_CHECK_ARG(n_chunks <= 65535, "sesa_frame_chunks: too many chunks in one call (%d)", n_chunks);
+  dim3 grid((unsigned)min((int64_t)256, ceil_div64(chunk_size, 256)), channels, n_chunks);
+  frame_chunks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mix, mix_len, channels, starts, lens, modes,
+                                                              chunk_size, chunks);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Overlap-add as a GATHER: each output sample sums the chunks that cover it in ascending chunk order
+// with separate multiply and add, which is the order and rounding of the reference's
+// `result[...] += x * window; counter[...] += window` loop (utils.py:439-442).
+__device__ __forceinline__ float demix_window(const float* __restrict__ w, int64_t o, int64_t L, int fade, int kind) {
+  if (kind == 1 && o < fade) return 1.0f;
+  if (kind == 2 && o >= L - fade) return 1.0f;
+  return w[o];
+}
+
+__global__ void overlap_add_kernel(const float* __restrict__ y, const int64_t* __restrict__ starts,
+                                   const int64_t* __restrict__ lens, const int32_t* __restrict__ kinds,
+                                   int n_chunks, int64_t step, int64_t L, int fade,
+                                   const float* __restrict__ window, int nstems, int channels,
+                                   int64_t padded_len, int64_t crop, int64_t out_len,
+                                   float* __restrict__ result, float* __restrict__ counter) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = counter ? padded_len : out_len;
+  if (i >= total) return;
+  const int64_t p = counter ? i : i + crop;  // padded coordinate
+  int64_t k_hi = p / step;
+  if (k_hi > n_chunks - 1) k_hi = n_chunks - 1;
+  int64_t k_lo = (p - L + step) / step;  // ceil((p - L + 1)/step) for p-L+1 > 0
+  if (p - L + 1 <= 0) k_lo = 0;
+  float cnt = 0.f;
+  for (int64_t k = k_lo; k <= k_hi; ++k) {
+    const int64_t o = p - starts[k];
+    if (o < 0 || o >= lens[k]) continue;
+    cnt = __fadd_rn(cnt, demix_window(window, o, L, fade, kinds[k]));
+  }
+  if (counter) counter[p] = cnt;
+  const int64_t io = p - crop;
+  if (io < 0 || io >= out_len) return;
+  const int nc = nstems * channels;
+  for (int sc = 0; sc < nc; ++sc) {
+    float acc = 0.f;
+    for (int64_t k = k_lo; k <= k_hi; ++k) {
+      const int64_t o = p - starts[k];
+      if (o < 0 || o >= lens[k]) continue;
+      const float w = demix_window(window, o, L, fade, kinds[k]);
+      acc = __fadd_rn(acc, __fmul_rn(y[((int64_t)k * nc + sc) * L + o], w));
+    }
+    float r = acc / cnt;
+    if (r != r) r = 0.f;  // nan_to_num(nan=0) of 0/0 (utils.py:459)
+    result[(int64_t)sc * out_len + io] = r;
+  }
+}
+
+extern "C" int sesa_overlap_add(const float* chunk_out, const int64_t* starts, const int64_t* lens,
+                                const int32_t* kinds, int n_chunks, int64_t step, int64_t chunk_size, int fade,
+                                const float* window, int nstems, int channels, int64_t padded_len,
+                                int64_t crop, int64_t out_len, float* result, float* counter, void* stream) {
+  SESA_CHECK_ARG(step > 0 && chunk_size >= step, "sesa_overlap_add: bad step %lld", (long long)step);
+  SESA_CHECK_ARG(crop >= 0 && crop + out_len <= padded_len, "sesa_overlap_add: crop range outside the padded mix");
+  const int64_t total = counter ? padded_len : out_len;
+  if (total == 0) return SESA_OK;
+  overlap_add_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      chunk_out, starts, lens, kinds, n_chunks, step, chunk_size, fade, window, nstems, channels, padded_len,
+      crop, out_len, result, counter);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                      float* __restrict__ y, int64_t rows, int dim, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * dim;
+  float ss = 0.f;
+  for (int i = lane; i < dim; i += 32) ss += xr[i] * xr[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  float* yr = y + row * dim;
+  for (int i = lane; i < dim; i += 32) yr[i] = xr[i] * inv * scale * gamma[i];
+}
+
+extern "C" int sesa_rmsnorm(const float* x, const float* gamma, float* y, int64_t rows, int dim, void* stream) {
+  if (rows == 0) return SESA_OK;
+  rmsnorm_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, y, rows, dim,
+                                                                                  sqrtf((float)dim));
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += x[i];
+}
+
+extern "C" int sesa_add_inplace(float* y, const float* x, int64_t n, void* stream) {
+  if (n == 0) return SESA_OK;
+  add_inplace_kernel<<<(unsigned)min((int64_t)148 * 16, ceil_div64(n, 256)), 256, 0, (cudaStream_t)stream>>>(y, x, n);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ in, const int32_t* __restrict__ idx,
+                                   float* __restrict__ out, int n_in, int n_out, int width) {
+  const int64_t r = blockIdx.y;
+  const float* src = in + r * (int64_t)n_in * width;
+  float* dst = out + r * (int64_t)n_out * width;
+  const int total = n_out * width;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    dst[i] = src[idx[i / width] * width + (i % width)];
+}
+
+extern "C" int sesa_gather_rows(const float* in, const int32_t* idx, float* out, int64_t rows, int n_in,
+                                int n_out, int width, void* stream) {
+  if (rows == 0 || n_out == 0) return SESA_OK;
+  SESA_CHECK_ARG(rows <= 65535LL * 32768, "sesa_gather_rows: too many rows");
+  int64_t done = 0;
+  while (done < rows) {  // gridDim.y limit
+    const int64_t nr = min((int64_t)65535, rows - done);
+    dim3 grid((unsigned)min(8, (n_out * width + 255) / 256), (unsigned)nr);
+    gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in + done * (int64_t)n_in * width, idx,
+                                                                out + done * (int64_t)n_out * width, n_in,
+                                                                n_out, width);
+    SESA_LAUNCH_CHECK();
+    done += nr;
+  }
+  return SESA_OK;
+}

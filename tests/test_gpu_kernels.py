@@ -1,0 +1,190 @@
+"""GPU: each kernel of the C-ABI against a plain torch fp32 statement of the same op."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import max_rel, snr_db
+
+pytestmark = pytest.mark.gpu
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def S():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from sesa_audio_separation_b200 import _lib
+    _lib.require_cuda()
+    return _lib
+
+
+def _tw(n, dev):
+    from sesa_audio_separation_b200.roformer import _twiddle
+    return _twiddle(n).to(dev)
+
+
+@pytest.mark.parametrize('n_fft,hop,C,L', [(2048, 441, 2, 441 * 30), (2048, 512, 1, 20000), (1024, 256, 2, 256 * 31),
+                                           (8192, 1024, 2, 1024 * 15), (256, 64, 2, 5000)])
+def test_stft_matches_torch(lib, n_fft, hop, C, L):
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, C, L, generator=g)
+    win = torch.hann_window(n_fft)
+    ref = torch.stft(x.reshape(-1, L), n_fft=n_fft, hop_length=hop, window=win, return_complex=True)
+    T, F = ref.shape[-1], n_fft // 2 + 1
+    ref = torch.view_as_real(ref).reshape(3, C, F, T, 2).permute(0, 3, 2, 1, 4).contiguous()  # b t f c ri
+    xd = x.to(dev)
+    spec = torch.empty(3 * T, F * C * 2, device=dev)
+    lib.call('sesa_stft', P(xd), P(spec), P(win.to(dev)), P(_tw(n_fft, dev)), 3, C, L, n_fft, hop, 0, F, S())
+    got = spec.cpu().reshape(3, T, F, C, 2)
+    assert max_rel(ref.numpy(), got.numpy()) < 2e-6
+    # layout 1 (MDX23C planes)
+    dim_f = n_fft // 2
+    spec1 = torch.empty(3, C * 2, dim_f, T, device=dev)
+    lib.call('sesa_stft', P(xd), P(spec1), P(win.to(dev)), P(_tw(n_fft, dev)), 3, C, L, n_fft, hop, 1, dim_f, S())
+    ref1 = ref[:, :, :dim_f].permute(0, 3, 4, 2, 1).reshape(3, C * 2, dim_f, T)
+    assert max_rel(ref1.numpy(), spec1.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize('n_fft,hop,C,L,nst', [(2048, 441, 2, 441 * 30, 1), (2048, 512, 1, 20000, 2), (1024, 256, 2, 256 * 31, 2)])
+def test_mask_istft_matches_torch(lib, n_fft, hop, C, L, nst):
+    from sesa_audio_separation_b200.roformer import _istft_envelope
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(2)
+    B = 2
+    x = torch.randn(B, C, L, generator=g)
+    win = torch.hann_window(n_fft)
+    z = torch.stft(x.reshape(-1, L), n_fft=n_fft, hop_length=hop, window=win, return_complex=True)
+    F, T = z.shape[-2:]
+    z = z.reshape(B, C, F, T)
+    mask = torch.randn(nst, B, T, F, C, 2, generator=g)
+    mc = torch.view_as_complex(mask).permute(1, 0, 4, 3, 2)            # b n c f t
+    prod = z[:, None] * mc
+    ref = torch.istft(prod.reshape(-1, F, T), n_fft=n_fft, hop_length=hop, window=win, length=L).reshape(B, nst, C, L)
+    spec = torch.view_as_real(z).permute(0, 3, 2, 1, 4).contiguous().to(dev)    # b t f c ri
+    out = torch.empty(B, nst, C, L, device=dev)
+    env = _istft_envelope(win, n_fft, hop, T, L).to(dev)
+    lib.call('sesa_mask_istft', P(spec), P(mask.to(dev)), None, None, P(out), P(win.to(dev)), P(env),
+             P(_tw(n_fft, dev)), B, nst, C, n_fft, hop, T, L, 0, 0, S())
+    assert max_rel(ref.numpy(), out.cpu().numpy()) < 3e-6
+    assert snr_db(ref.numpy(), out.cpu().numpy()) > 110
+
+
+def _run_gemm(lib, A, W, bias, Cbuf, ep_kwargs, M, N, K, lda, ldc):
+    from sesa_audio_separation_b200.roformer import _GroupTable, _epilogue
+    tab = _GroupTable([dict(A=A.data_ptr(), W=W.data_ptr(), bias=bias.data_ptr() if bias is not None else 0,
+                            C=Cbuf.data_ptr(), M=M, N=N, K=K, lda=lda, ldw=W.shape[1], ldc=ldc)], A.device)
+    ep = _epilogue(**ep_kwargs)
+    lib.call('sesa_gemm_simt', P(tab.dev), tab.n, tab.max_m, tab.max_n, ctypes.byref(ep), S())
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 512, 512), (257, 130, 10), (1000, 1544, 64), (77, 16, 2048), (513, 1032, 96)])
+def test_gemm_simt_plain_bias_act(lib, M, N, K):
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    for act, fn in ((0, lambda v: v), (1, torch.nn.functional.gelu), (2, torch.tanh)):
+        Cb = torch.zeros(M, N, device=dev)
+        _run_gemm(lib, A, W, b, Cb, dict(act=act), M, N, K, K, N)
+        ref = fn(A.double() @ W.double().T + b.double())
+        assert max_rel(ref.cpu().numpy(), Cb.cpu().numpy()) < 3e-6, act
+
+
+def test_gemm_simt_rownorm_residual_glu_rotary(lib):
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(4)
+    M, N, K = 333, 264, 48
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    # rownorm + residual
+    C0 = torch.randn(M, N, generator=g).to(dev)
+    Cb = C0.clone()
+    _run_gemm(lib, A, W, b, Cb, dict(rownorm=1, residual=1), M, N, K, K, N)
+    ref = C0.double() + torch.nn.functional.normalize(A.double(), dim=-1) @ W.double().T + b.double()
+    assert max_rel(ref.cpu().numpy(), Cb.cpu().numpy()) < 3e-6
+    # GLU with interleaved rows
+    half = N // 2
+    Wi = torch.stack([W[:half], W[half:]], 1).reshape(N, K).contiguous()
+    bi = torch.stack([b[:half], b[half:]], 1).reshape(N).contiguous()
+    Cg = torch.zeros(M, half, device=dev)
+    _run_gemm(lib, A, Wi, bi, Cg, dict(glu=1), M, N, K, K, half)
+    ref = torch.nn.functional.glu(A.double() @ W.double().T + b.double(), dim=-1)
+    assert max_rel(ref.cpu().numpy(), Cg.cpu().numpy()) < 3e-6
+    # rotary on the first 128 columns, positions (m // 3) % 37
+    from oracle.third_party import apply_rotary
+    freqs = 1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64))
+    ang = torch.einsum('i,j->ij', torch.arange(37, dtype=torch.float32), freqs)
+    rot = torch.stack([ang.cos(), ang.sin()], -1).contiguous().to(dev)
+    Cr = torch.zeros(M, N, device=dev)
+    _run_gemm(lib, A, W, None, Cr, dict(rot=rot, rot_cols=128, rot_dim=64, pos_div=3, pos_mod=37), M, N, K, K, N)
+    plain = (A.double() @ W.double().T).float().cpu()
+    pos = (torch.arange(M) // 3) % 37
+    full = torch.einsum('i,j->ij', pos.float(), freqs).repeat_interleave(2, -1)
+    ref = plain.clone()
+    for h in range(2):
+        blk = plain[:, h * 64:(h + 1) * 64]
+        rh = torch.stack((-blk[:, 1::2], blk[:, 0::2]), -1).reshape(M, 64)
+        ref[:, h * 64:(h + 1) * 64] = blk * full.cos() + rh * full.sin()
+    assert max_rel(ref.numpy(), Cr.cpu().numpy()) < 3e-6
+
+
+@pytest.mark.parametrize('axis', [0, 1])
+def test_attention_simt(lib, axis):
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(5)
+    B, T, F, H, dh = 2, 150, 20, 3, 64
+    inner = H * dh
+    ld = (3 * inner + H + 3) // 4 * 4
+    qkv = torch.randn(B * T * F, ld, generator=g)
+    out = torch.zeros(B * T * F, inner, device=dev)
+    if axis == 0:
+        args = (B * F, T, F, T * F, 1, F)
+    else:
+        args = (B * T, F, 1, F, 0, 1)
+    lib.call('sesa_attention_simt', P(qkv.to(dev)), P(out), ld, inner, H, dh, *args, S())
+    x = qkv.reshape(B, T, F, ld)
+    q = x[..., :inner].reshape(B, T, F, H, dh)
+    k = x[..., inner:2 * inner].reshape(B, T, F, H, dh)
+    v = x[..., 2 * inner:3 * inner].reshape(B, T, F, H, dh)
+    gate = x[..., 3 * inner:3 * inner + H].sigmoid()
+    if axis == 0:
+        sim = torch.einsum('bifhd,bjfhd->bfhij', q.double(), k.double())
+        o = torch.einsum('bfhij,bjfhd->bifhd', sim.softmax(-1), v.double())
+    else:
+        sim = torch.einsum('btihd,btjhd->bthij', q.double(), k.double())
+        o = torch.einsum('bthij,btjhd->btihd', sim.softmax(-1), v.double())
+    ref = (o * gate.double()[..., None]).reshape(B * T * F, inner)
+    assert max_rel(ref.numpy(), out.cpu().numpy()) < 3e-6
+
+
+def test_rmsnorm_gather_add(lib):
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1000, 384, generator=g).to(dev)
+    gamma = torch.randn(384, generator=g).to(dev)
+    y = torch.empty_like(x)
+    lib.call('sesa_rmsnorm', P(x), P(gamma), P(y), 1000, 384, S())
+    ref = torch.nn.functional.normalize(x, dim=-1) * math.sqrt(384) * gamma
+    assert max_rel(ref.cpu().numpy(), y.cpu().numpy()) < 1e-6
+    src = torch.randn(50, 30, 2, generator=g).to(dev)
+    idx = torch.randint(0, 30, (45,), generator=g).to(torch.int32).to(dev)
+    dst = torch.empty(50, 45, 2, device=dev)
+    lib.call('sesa_gather_rows', P(src), P(idx), P(dst), 50, 30, 45, 2, S())
+    assert torch.equal(dst, src[:, idx.long()])
+    a = torch.randn(5000, generator=g).to(dev)
+    b = torch.randn(5000, generator=g).to(dev)
+    ref = a + b
+    lib.call('sesa_add_inplace', P(a), P(b), 5000, S())
+    assert torch.equal(a, ref)

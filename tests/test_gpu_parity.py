@@ -1,0 +1,129 @@
+"""GPU: model forward and demix parity against the committed golden vectors (produced by the
+unmodified reference) and against the CPU oracle, all through the C-ABI."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, max_rel, snr_db
+from oracle import demix as odemix
+from oracle.cases import CASES, DEMIX_IDENTITY_CASES, DEMIX_MODEL_CASES, make_input
+from oracle.weights import fill_state_dict, synth_mix
+
+pytestmark = pytest.mark.gpu
+
+# fp32 parity gate of BASELINE.json's north_star
+FP32_MAX_REL = 1e-4
+FP32_SNR_DB = 60.0
+
+
+def build(case):
+    import sesa_audio_separation_b200 as sesa
+    kind, cfg = case['kind'], dict(case['cfg'])
+    if kind == 'bs_roformer':
+        if 'freqs_per_bands' in cfg:
+            cfg['freqs_per_bands'] = tuple(cfg['freqs_per_bands'])
+        m = sesa.BSRoformer(**cfg)
+    elif kind == 'mel_band_roformer':
+        m = sesa.MelBandRoformer(**cfg)
+    else:
+        from sesa_audio_separation_b200.mdx23c import TFC_TDF_net
+        m = TFC_TDF_net(sesa.ConfigDict(cfg))
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, case['seed'])
+    m.load_state_dict(sd)
+    return m.eval().to('cuda'), sd
+
+
+@pytest.mark.parametrize('name', [n for n in CASES if CASES[n]['kind'] != 'mdx23c'])
+def test_forward_matches_reference_golden(manifest, name):
+    case = CASES[name]
+    model, sd = build(case)
+    assert {k: list(v.shape) for k, v in sd.items()} == manifest[name]['shapes']
+    y = model(make_input(case).cuda()).cpu().numpy()
+    ref = golden(name)['y']
+    assert y.shape == ref.shape
+    print(name, 'max_rel', max_rel(ref, y), 'snr', snr_db(ref, y))
+    assert max_rel(ref, y) <= FP32_MAX_REL
+    assert snr_db(ref, y) >= FP32_SNR_DB
+
+
+class Identity:
+    pass
+
+
+def _identity_model():
+    from sesa_audio_separation_b200.module import KernelModule
+
+    class Ident(KernelModule):
+        def forward(self, x, **kw):
+            return x.clone()
+    return Ident()
+
+
+def test_demix_identity_bit_exact_and_counter():
+    import sesa_audio_separation_b200 as sesa
+    g = golden('demix_identity')
+    for i, (length, L, ov, bs) in enumerate(DEMIX_IDENTITY_CASES):
+        cfg = sesa.ConfigDict(dict(audio=dict(chunk_size=L), inference=dict(num_overlap=ov, batch_size=bs),
+                                   training=dict(instruments=['a'], target_instrument='a')))
+        mix = synth_mix(length, 2, seed=100 + i)
+        for eb in (1, 3):
+            eng = sesa.DemixEngine(cfg, _identity_model(), 'cuda', engine_batch=eb)
+            est, cnt = eng.run(mix, return_counter=True)
+            assert np.array_equal(est[0], g[f'case{i}']), (i, length, L, ov, bs, eb)
+            _, ocnt = odemix.demix(mix, lambda a: a, L, ov, bs, 1, return_counter=True)
+            assert np.array_equal(cnt, ocnt[0, 0]), ('counter', i)
+
+
+@pytest.mark.parametrize('name', list(DEMIX_MODEL_CASES))
+def test_demix_matches_reference_golden(name):
+    import sesa_audio_separation_b200 as sesa
+    dc = DEMIX_MODEL_CASES[name]
+    case = CASES[dc['model']]
+    model, _ = build(case)
+    cfg = sesa.ConfigDict(dict(audio=dict(chunk_size=dc['chunk_size']),
+                               inference=dict(num_overlap=dc['num_overlap'], batch_size=dc['batch_size']),
+                               training=dict(instruments=dc['instruments'], target_instrument=dc['target'])))
+    mix = synth_mix(dc['length'], 2, seed=dc['seed'])
+    res = sesa.demix(cfg, model, mix, 'cuda', case['kind'], engine_batch=3)
+    g = golden(name)
+    assert list(res.keys()) == list(g.keys())
+    for k in res:
+        print(name, k, 'max_rel', max_rel(g[k], res[k]), 'snr', snr_db(g[k], res[k]))
+        assert res[k].shape == g[k].shape
+        assert max_rel(g[k], res[k]) <= FP32_MAX_REL
+        assert snr_db(g[k], res[k]) >= FP32_SNR_DB
+
+
+def test_progress_protocol(capsys):
+    import sesa_audio_separation_b200 as sesa
+    cfg = sesa.ConfigDict(dict(audio=dict(chunk_size=1000), inference=dict(num_overlap=2, batch_size=1),
+                               training=dict(instruments=['a'], target_instrument='a')))
+    backend = type('B', (), {'model': _identity_model()})()
+    sesa.demix_pytorch_optimized(cfg, backend, synth_mix(5000, 2, seed=1), 'cuda')
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith('[SESA_PROGRESS]')]
+    vals = [int(l[len('[SESA_PROGRESS]'):]) for l in lines]
+    assert vals[-1] == 100 and vals == sorted(vals)
+
+
+def test_full_size_bs_roformer_chunk_vs_oracle_on_gpu():
+    """BASELINE C2 model (dim 512, depth 12, 62 bands) on one full 352800-sample chunk against the oracle
+    restatement evaluated in true fp32 on the same GPU (TF32 off) — the oracle itself is pinned on CPU."""
+    import sesa_audio_separation_b200 as sesa
+    from oracle import roformer as orof
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = dict(dim=512, depth=12, stereo=True, num_stems=1, time_transformer_depth=1, freq_transformer_depth=1,
+               dim_head=64, heads=8, stft_n_fft=2048, stft_hop_length=441, stft_win_length=2048,
+               mask_estimator_depth=2)
+    model = sesa.BSRoformer(**cfg)
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=3)
+    model.load_state_dict(sd)
+    model.eval().to('cuda')
+    x = torch.from_numpy(synth_mix(352800, 2, seed=9))[None].cuda()
+    y = model(x).cpu().numpy()
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    with torch.inference_mode():
+        ref = orof.bs_roformer_forward(sd_gpu, cfg, x).cpu().numpy()
+    print('full-size BS chunk: max_rel', max_rel(ref, y), 'snr', snr_db(ref, y))
+    assert max_rel(ref, y) <= FP32_MAX_REL
+    assert snr_db(ref, y) >= FP32_SNR_DB

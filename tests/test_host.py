@@ -1,0 +1,108 @@
+"""CPU: host logic, the C-ABI library's exported symbols, and the no-fallback rule."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+from oracle import demix as odemix
+from oracle.cases import DEMIX_IDENTITY_CASES
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from sesa_audio_separation_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'sesa_b200.h')).read()
+    declared = set(re.findall(r'\b(sesa_[a-z0-9_]+)\s*\(', header))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/sesa_b200.h but not exported'
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.sesa_abi_version() == 1
+
+
+def test_plan_matches_oracle_schedule():
+    from sesa_audio_separation_b200.plan import make_plan
+    kinds = {'both': 0, 'nofadein': 1, 'nofadeout': 2}
+    modes = {'constant': 0, 'reflect': 1}
+    cases = list(DEMIX_IDENTITY_CASES) + [(7938000, 352800, 4, 1), (7938000, 352800, 4, 2), (1323000, 261120, 4, 1),
+                                          (26460000, 352800, 2, 4)]
+    for length, L, ov, bs in cases:
+        p = make_plan(length, L, ov, bs)
+        o = odemix.demix_schedule(length, L, ov, bs)
+        assert (p.step, p.border, p.fade, p.padded, p.pad) == (o['step'], o['border'], o['fade'], o['padded'], o['pad'])
+        assert list(zip(p.starts, p.lens, p.modes, p.kinds)) == [(s, l, modes[m], kinds[w]) for s, l, m, w in o['chunks']]
+    p = make_plan(7938000, 352800, 4, 1)
+    assert p.n_chunks == 96 and p.padded == 8467200 and p.lens[-3:] == [264600, 176400, 88200]
+    assert make_plan(1323000, 261120, 4, 1).n_chunks == 27
+
+
+def test_window_is_torch_linspace():
+    from sesa_audio_separation_b200.plan import windowing_array
+    w = windowing_array(352800, 35280)
+    assert torch.equal(w, odemix.windowing_array(352800, 35280))
+
+
+def test_state_dict_layout_matches_reference_manifest(manifest):
+    import sesa_audio_separation_b200 as sesa
+    from oracle.cases import CASES
+    for name, case in CASES.items():
+        cfg = dict(case['cfg'])
+        if case['kind'] == 'bs_roformer':
+            if 'freqs_per_bands' in cfg:
+                cfg['freqs_per_bands'] = tuple(cfg['freqs_per_bands'])
+            m = sesa.BSRoformer(**cfg)
+        elif case['kind'] == 'mel_band_roformer':
+            m = sesa.MelBandRoformer(**cfg)
+        else:
+            continue
+        assert {k: list(v.shape) for k, v in m.state_dict().items()} == manifest[name]['shapes']
+
+
+def test_mel_band_maps_bit_exact():
+    from sesa_audio_separation_b200.roformer import mel_band_maps
+    g = golden('mel_small')
+    fi, nfpb, nbpf, _ = mel_band_maps(44100, 2048, 60, True)
+    assert np.array_equal(fi, g['freq_indices'])
+    assert np.array_equal(nfpb, g['num_freqs_per_band'])
+    assert np.array_equal(nbpf, g['num_bands_per_freq'])
+
+
+def test_no_cpu_fallback():
+    import sesa_audio_separation_b200 as sesa
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    m = sesa.BSRoformer(64, depth=1, stereo=True, heads=1, time_transformer_depth=1, freq_transformer_depth=1)
+    with pytest.raises(sesa.SesaError):
+        m(torch.zeros(1, 2, 4410))
+    cfg = sesa.ConfigDict(dict(audio=dict(chunk_size=1000), inference=dict(num_overlap=2, batch_size=1),
+                               training=dict(instruments=['a'], target_instrument='a')))
+    with pytest.raises(sesa.SesaError):
+        sesa.demix(cfg, m, np.zeros((2, 5000), np.float32), 'cpu', 'bs_roformer')
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'sesa_audio_separation_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), fn
+
+
+def test_config_loading_with_python_tuple(tmp_path):
+    import sesa_audio_separation_b200 as sesa
+    p = tmp_path / 'c.yaml'
+    p.write_text('audio: {chunk_size: 352800}\nmodel:\n  dim: 64\n  depth: 1\n  stereo: true\n  heads: 1\n'
+                 '  time_transformer_depth: 1\n  freq_transformer_depth: 1\n'
+                 '  freqs_per_bands: !!python/tuple [512, 513]\n'
+                 'training: {instruments: [vocals, other], target_instrument: vocals}\n'
+                 'inference: {batch_size: 1, num_overlap: 4}\n')
+    model, cfg = sesa.get_model_from_config('bs_roformer', str(p))
+    assert cfg.audio.chunk_size == 352800 and model.num_bands == 2
+    assert sesa.prefer_target_instrument(cfg) == ['vocals']
+    with pytest.raises(ValueError):
+        sesa.get_model_from_config('scnet', str(p))
