@@ -82,8 +82,41 @@ def check(status):
         raise SesaError(f'sesa_b200 error {status}: {msg.decode() if msg else "?"}')
 
 
+# ---- launch accounting / per-kernel-class timing (bench.py, profiling); off by default
+LAUNCHES = 0
+_profile = None   # dict: class -> [ (start_event, end_event), ... ] when enabled
+_CLASS = {'sesa_gemm_simt': 'gemm', 'sesa_gemm_tc': 'gemm', 'sesa_attention_simt': 'attention',
+          'sesa_attention_tc': 'attention', 'sesa_stft': 'stft', 'sesa_mask_istft': 'mask_istft',
+          'sesa_overlap_add': 'overlap_add', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}
+
+
+def profile_start():
+    global _profile
+    _profile = {}
+
+
+def profile_stop():
+    """Returns {class: (n_launches, total_ms)} measured with CUDA events on the launch stream."""
+    global _profile
+    import torch
+    torch.cuda.synchronize()
+    out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in _profile.items()}
+    _profile = None
+    return out
+
+
 def call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    if _profile is None:
+        check(getattr(load(), name)(*args))
+        return
+    import torch
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
     check(getattr(load(), name)(*args))
+    b.record()
+    _profile.setdefault(_CLASS.get(name, 'other'), []).append((a, b))
 
 
 def require_cuda():

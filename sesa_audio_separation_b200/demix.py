@@ -94,7 +94,8 @@ class DemixEngine:
         last_pct = -1
         while k < hi:
             nb = min(EB, hi - k)
-            call('sesa_frame_chunks', _ptr(padded), plan.padded, C, _ptr(starts[k:]), _ptr(lens[k:]), _ptr(modes[k:]),
+            call('sesa_frame_chunks', _ptr(padded), plan.padded, C, _ptr(starts) if k == 0 else ctypes.c_void_p(starts.data_ptr() + 8 * k),
+                 ctypes.c_void_p(lens.data_ptr() + 8 * k), ctypes.c_void_p(modes.data_ptr() + 4 * k),
                  nb, L, _ptr(chunks), st)
             y = self.model.forward(chunks[:nb])
             y = y.reshape(nb, n_inst, C, -1)
@@ -111,9 +112,10 @@ class DemixEngine:
         crop = plan.border if plan.pad else 0
         result = torch.empty(n_inst, C, length, device=dev, dtype=torch.float32)
         counter = torch.empty(plan.padded, device=dev, dtype=torch.float32) if return_counter else None
+        window = windowing_array(L, plan.fade).to(dev)
         if self.world == 1:
             call('sesa_overlap_add', _ptr(chunk_out), _ptr(starts), _ptr(lens), _ptr(kinds), plan.n_chunks, plan.step,
-                 L, plan.fade, _ptr(windowing_array(L, plan.fade).to(dev)), n_inst, C, plan.padded, crop, length,
+                 L, plan.fade, _ptr(window), n_inst, C, plan.padded, crop, length,
                  _ptr(result), _ptr(counter), st)
         else:
             from .distributed import sharded_overlap_add
