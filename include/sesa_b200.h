@@ -100,6 +100,44 @@ int sesa_add_inplace(float* y, const float* x, int64_t n, void* stream);
 int sesa_gather_rows(const float* in, const int32_t* idx, float* out, int64_t rows, int n_in, int n_out,
                      int width, void* stream);
 
+/* ---- tensor-core (tcgen05 / TMEM / TMA) dense math ------------------------------------------ */
+/* Operands of the tensor-core kernels are bf16 "planes": plane 0 = bf16(x) ("hi"), plane 1 = bf16(x - hi) ("lo").
+ * nsplit = 3 evaluates A.W^T as Ahi.Whi + Ahi.Wlo + Alo.Whi with fp32 accumulation in TMEM (~16 significant
+ * bits per operand: the fp32-parity mode of BASELINE.json); nsplit = 1 uses the hi planes only (bf16 mode). */
+typedef struct sesa_tc_problem {
+  const void* A;         /* bf16 [planes][M][lda]; lda % 8 == 0, 16-byte aligned */
+  const void* W;         /* bf16 [planes][N][ldw] (nn.Linear layout); ldw % 8 == 0 */
+  const float* bias;     /* [N] or NULL */
+  const float* rowscale; /* [M] or NULL: acc[m,:] *= rowscale[m] before the bias (fused RMSNorm) */
+  float* C;              /* fp32 output [M][ldc] or NULL */
+  void* P;               /* bf16 plane output [out_planes][M][ldp] or NULL (feeds the next tensor-core op) */
+  int64_t lda, a_plane, ldw, w_plane, ldc, ldp, p_plane; /* element strides; *_plane = plane-to-plane distance */
+  int32_t M, N, K, _pad;
+} sesa_tc_problem;
+
+/* Bytes of the device-side group table for n_groups problems. */
+int64_t sesa_gemm_tc_table_bytes(int n_groups);
+/* Encode the TMA tensor maps and tile ranges of n_groups problems into table_host (host memory of
+ * sesa_gemm_tc_table_bytes(n_groups) bytes); the caller copies the table to the device and keeps it while
+ * the pointers stay valid.  *total_tiles receives the number of 128 x block_n output tiles. */
+int sesa_gemm_tc_build(const sesa_tc_problem* problems_host, int n_groups, int block_n, void* table_host,
+                       int* total_tiles);
+/* Grouped GEMM on the 5th-gen tensor cores (nn.Linear call sites bs_roformer.py:63,67,99,104,237,264):
+ * TMA-fed, tcgen05.mma into TMEM, persistent over tiles.  Epilogue fields of sesa_gemm_epilogue apply except
+ * `rownorm` (use sesa_tc_problem.rowscale).  block_n in {128, 256}; nsplit in {1, 3}; out_planes in {1, 2}. */
+int sesa_gemm_tc(const void* table_dev, int n_groups, int total_tiles, int block_n, int nsplit, int out_planes,
+                 const sesa_gemm_epilogue* ep_host, void* stream);
+/* Row preparation for the tensor-core GEMMs: per row r of x[rows][dim] (row stride ldx)
+ *   inv = normalize ? 1/max(||x_r||_2, 1e-12) : 1                 (F.normalize of RMSNorm, bs_roformer.py:49)
+ *   planes[p][r][:] = bf16 split of x_r * inv                      (p < out_planes, row stride ldp)
+ *   gates[r][h] = (x_r * inv) . gate_w[h] + gate_b[h], h < n_gates (to_gates logits, bs_roformer.py:117; optional)
+ *   rowinv[r] = inv                                                (optional) */
+int sesa_prep_rows(const float* x, int64_t ldx, int64_t rows, int dim, int normalize, void* planes, int64_t ldp,
+                   int64_t p_plane, int out_planes, const float* gate_w, const float* gate_b, int n_gates,
+                   float* gates, int64_t ldg, float* rowinv, void* stream);
+/* bf16 hi/lo planes of a weight matrix w[rows][cols] -> planes[2][rows][ldp] (zero padded to ldp). */
+int sesa_split_weight(const float* w, int64_t rows, int64_t cols, void* planes, int64_t ldp, void* stream);
+
 /* ---- windowed overlap-add of chunk outputs (utils.py:432-464) ------------------------------- */
 /* chunk_out[k][n][c][L]; result[n][c][out_len] = sum_k (ascending) y*w / sum_k w over padded positions
  * p = crop + i, NaN -> 0.  window[L] is _getWindowingArray (utils.py:295-327); kinds[k]: 0 both ramps,

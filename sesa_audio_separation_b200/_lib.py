@@ -31,6 +31,13 @@ GEMM_GROUP_DTYPE = np.dtype([('A', '<u8'), ('W', '<u8'), ('bias', '<u8'), ('C', 
                              ('lda', '<i8'), ('ldw', '<i8'), ('ldc', '<i8')])
 assert GEMM_GROUP_DTYPE.itemsize == 72
 
+# numpy mirror of struct sesa_tc_problem (120 bytes)
+TC_PROBLEM_DTYPE = np.dtype([('A', '<u8'), ('W', '<u8'), ('bias', '<u8'), ('rowscale', '<u8'), ('C', '<u8'),
+                             ('P', '<u8'), ('lda', '<i8'), ('a_plane', '<i8'), ('ldw', '<i8'), ('w_plane', '<i8'),
+                             ('ldc', '<i8'), ('ldp', '<i8'), ('p_plane', '<i8'),
+                             ('M', '<i4'), ('N', '<i4'), ('K', '<i4'), ('_pad', '<i4')])
+assert TC_PROBLEM_DTYPE.itemsize == 120
+
 _SIGS = {
     'sesa_abi_version': (c_int, []),
     'sesa_last_error': (c_char_p, []),
@@ -45,6 +52,12 @@ _SIGS = {
     'sesa_gemm_simt': (c_int, [c_void_p, c_int, c_int, c_int, POINTER(GemmEpilogue), c_void_p]),
     'sesa_attention_simt': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int64, c_int64, c_int64, c_void_p]),
+    'sesa_gemm_tc_table_bytes': (c_int64, [c_int]),
+    'sesa_gemm_tc_build': (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_int)]),
+    'sesa_gemm_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(GemmEpilogue), c_void_p]),
+    'sesa_prep_rows': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_int64, c_int,
+                               c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    'sesa_split_weight': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     'sesa_rmsnorm': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'sesa_add_inplace': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     'sesa_gather_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
@@ -85,7 +98,7 @@ def check(status):
 # ---- launch accounting / per-kernel-class timing (bench.py, profiling); off by default
 LAUNCHES = 0
 _profile = None   # dict: class -> [ (start_event, end_event), ... ] when enabled
-_CLASS = {'sesa_gemm_simt': 'gemm', 'sesa_gemm_tc': 'gemm', 'sesa_attention_simt': 'attention',
+_CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_attention_simt': 'attention',
           'sesa_attention_tc': 'attention', 'sesa_stft': 'stft', 'sesa_mask_istft': 'mask_istft',
           'sesa_overlap_add': 'overlap_add', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}
 

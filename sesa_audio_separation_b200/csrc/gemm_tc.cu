@@ -1,0 +1,532 @@
+// Grouped GEMM on the Blackwell 5th-generation tensor cores:  C = epi( A[M,K] . W[N,K]^T ).
+//
+// Serves the nn.Linear call sites of the RoFormer forward (bs_roformer.py:63,67 FeedForward; :99,104
+// to_qkv / to_out; :237 BandSplit; :264 MaskEstimator MLP).  Design (B200-first, not a translation of
+// anything in the reference, which only calls cuBLAS through PyTorch):
+//   * persistent CTAs (one per SM) walk a tile list that spans all problems of a grouped launch;
+//   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled 64-wide K slabs, mbarrier pipeline),
+//     warp 1 = single-thread tcgen05.mma issuer, accumulators in TMEM (two BN-column buffers, so the
+//     epilogue of tile i overlaps the main loop of tile i+1), warps 2-5 = epilogue (tcgen05.ld);
+//   * fp32 parity on bf16 tensor cores: operands are bf16 hi/lo planes and each K slab issues
+//     Ahi.Whi + Ahi.Wlo + Alo.Whi into the same fp32 TMEM accumulator (NSPLIT = 3); NSPLIT = 1 is plain bf16;
+//   * the epilogue fuses row scale (RMSNorm), bias, GELU/tanh/sigmoid, rotary embedding, GLU, residual add,
+//     and writes fp32 and/or the bf16 planes the next tensor-core op consumes.
+#include <string.h>
+
+#include "common.cuh"
+#include "sesa_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // one 128-byte swizzle row of bf16
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int MAX_GROUPS = 1024;
+
+struct alignas(128) TcGroup {
+  CUtensorMap mapA;  // dims (K, M, planes), box (64, 128, 1)
+  CUtensorMap mapW;  // dims (K, N, planes), box (64, BN, 1)
+  const float* bias;
+  const float* rowscale;
+  float* C;
+  __nv_bfloat16* P;
+  int64_t ldc, ldp, p_plane;
+  int32_t M, N, K, tile_begin;
+  int32_t n_blocks, k_blocks, tile_end, _r;
+};
+static_assert(sizeof(TcGroup) % 128 == 0, "table entries must keep the tensor maps 128-byte aligned");
+
+template <int BN, int NSPLIT>
+struct Cfg {
+  static constexpr int NP = NSPLIT == 3 ? 2 : 1;           // planes staged per operand
+  static constexpr int A_BYTES = BM * BK * 2;               // 16 KB per plane
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + MAX_GROUPS * 4;
+  static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: power of two
+};
+
+__device__ __forceinline__ float act_apply_tc(float v, int act) {
+  if (act == SESA_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  if (act == SESA_ACT_TANH) return tanhf(v);
+  if (act == SESA_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  return v;
+}
+
+__device__ __forceinline__ int find_group(const int* tile_end, int n_groups, int tile) {
+  int g = 0;
+  while (g + 1 < n_groups && tile >= tile_end[g]) ++g;
+  return g;
+}
+
+template <int BN, int NSPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles, sesa_gemm_epilogue ep,
+               int out_planes) {
+  using C = Cfg<BN, NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;         // [STAGES]
+  uint64_t* tmem_full = bars + 2 * C::STAGES;     // [2]
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  int* tile_end = reinterpret_cast<int*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < n_groups; i += NUM_THREADS) tile_end[i] = groups[i].tile_end;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      tc::mbar_init(&full_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(&tmem_full[a], 1);
+      tc::mbar_init(&tmem_empty[a], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (tc::elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
+        const int t = tile - g->tile_begin;
+        const int mb = t / g->n_blocks, nb = t % g->n_blocks;
+        const int kbs = g->k_blocks;
+        for (int kb = 0; kb < kbs; ++kb) {
+          tc::mbar_wait(&empty_bar[s], ph ^ 1);
+          tc::mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          uint8_t* sa = stage_base + s * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::NP * C::A_BYTES;
+#pragma unroll
+          for (int p = 0; p < C::NP; ++p) tc::tma_load_3d(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], kb * BK, mb * BM, p);
+#pragma unroll
+          for (int p = 0; p < C::NP; ++p) tc::tma_load_3d(sb + p * C::B_BYTES, &g->mapW, &full_bar[s], kb * BK, nb * BN, p);
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
+        const int kbs = g->k_blocks;
+        tc::mbar_wait(&tmem_empty[as], aph ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < kbs; ++kb) {
+          tc::mbar_wait(&full_bar[s], ph);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(stage_base + s * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::NP * C::A_BYTES;
+#pragma unroll
+          for (int prod = 0; prod < NSPLIT; ++prod) {
+            // products: (Ahi,Whi), (Ahi,Wlo), (Alo,Whi)
+            const uint32_t a_addr = sa + (prod == 2 ? C::A_BYTES : 0);
+            const uint32_t b_addr = sb + (prod == 1 ? C::B_BYTES : 0);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
+              const uint64_t bd = tc::make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
+              tc::umma_f16(d_tmem, ad, bd, idesc, (kb | prod | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc::umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+        tc::umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
+      const int t = tile - g->tile_begin;
+      const int mb = t / g->n_blocks, nb = t % g->n_blocks;
+      const int M = g->M, N = g->N;
+      const int m = mb * BM + q * 32 + lane;
+      const bool row_ok = m < M;
+      const int n0 = nb * BN;
+      const float* bias = g->bias;
+      float* Cp = g->C;
+      __nv_bfloat16* Pp = g->P;
+      const int64_t ldc = g->ldc, ldp = g->ldp, p_plane = g->p_plane;
+      const float rs = (g->rowscale != nullptr && row_ok) ? g->rowscale[m] : 1.0f;
+      int pos = 0;
+      if (ep.rot_cols > 0) pos = (m / ep.pos_div) % ep.pos_mod;
+      const bool c_vec = Cp != nullptr && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15) == 0;
+      const bool p_vec = Pp != nullptr && (ldp & 7) == 0 && (p_plane & 7) == 0 && (reinterpret_cast<uintptr_t>(Pp) & 15) == 0;
+
+      tc::mbar_wait(&tmem_full[as], aph);
+      tc::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= N) break;  // warp-uniform
+        float v[32];
+        tc::tmem_ld32(t_row + c * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j] * rs;
+          if (bias != nullptr && n + j < N) x += __ldg(bias + n + j);
+          v[j] = act_apply_tc(x, ep.act);
+        }
+        if (n < ep.rot_cols) {
+          const int half = ep.rot_dim >> 1;
+          const float2* rt = reinterpret_cast<const float2*>(ep.rot) + (int64_t)pos * half;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            if (n + j < ep.rot_cols) {
+              const float2 cs = __ldg(rt + (((n + j) % ep.rot_dim) >> 1));
+              const float x1 = v[j], x2 = v[j + 1];
+              v[j] = x1 * cs.x - x2 * cs.y;
+              v[j + 1] = x2 * cs.x + x1 * cs.y;
+            }
+          }
+        }
+        int width = 32, nbase = n, nlimit = N;
+        if (ep.glu) {  // rows of W interleaved (value, gate): out[:, n/2 + j] = v[2j] * sigmoid(v[2j+1])
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * (1.0f / (1.0f + expf(-v[2 * j + 1])));
+          width = 16;
+          nbase = n >> 1;
+          nlimit = N >> 1;
+        }
+        if (row_ok) {
+          const bool full = nbase + width <= nlimit;
+          if (Cp != nullptr) {
+            float* crow = Cp + (int64_t)m * ldc + nbase;
+            if (c_vec && full && (nbase & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (j < width) {
+                  float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                  if (ep.residual) {
+                    const float4 r = *reinterpret_cast<const float4*>(crow + j);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                    v[j] = o.x; v[j + 1] = o.y; v[j + 2] = o.z; v[j + 3] = o.w;  // planes carry the new stream
+                  }
+                  *reinterpret_cast<float4*>(crow + j) = o;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < width && nbase + j < nlimit) {
+                  if (ep.residual) v[j] += crow[j];
+                  crow[j] = v[j];
+                }
+              }
+            }
+          }
+          if (Pp != nullptr) {
+            __nv_bfloat16* prow = Pp + (int64_t)m * ldp + nbase;
+            if (p_vec && full && (nbase & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < width) {
+                  uint32_t hi[4], lo[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    tc::split_bf16(v[j + 2 * e], h0, l0);
+                    tc::split_bf16(v[j + 2 * e + 1], h1, l1);
+                    hi[e] = tc::pack_bf16(h0, h1);
+                    lo[e] = tc::pack_bf16(l0, l1);
+                  }
+                  *reinterpret_cast<uint4*>(prow + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  if (out_planes > 1) *reinterpret_cast<uint4*>(prow + p_plane + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < width && nbase + j < nlimit) {
+                  __nv_bfloat16 h, l;
+                  tc::split_bf16(v[j], h, l);
+                  prow[j] = h;
+                  if (out_planes > 1) prow[p_plane + j] = l;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN, int NSPLIT>
+int launch_gemm_tc(const TcGroup* table, int n_groups, int total_tiles, const sesa_gemm_epilogue& ep, int out_planes,
+                   cudaStream_t stream) {
+  using C = Cfg<BN, NSPLIT>;
+  static_assert(C::STAGES >= 2, "pipeline needs at least two stages");
+  static bool configured = false;
+  if (!configured) {
+    SESA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  int dev = 0, sms = 0;
+  SESA_CUDA(cudaGetDevice(&dev));
+  SESA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = total_tiles < sms ? total_tiles : sms;
+  gemm_tc_kernel<BN, NSPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(table, n_groups, total_tiles, ep, out_planes);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host side
+sesa_encode_tiled_fn sesa_get_encode_tiled() {
+  static sesa_encode_tiled_fn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<sesa_encode_tiled_fn>(p);
+  }
+  return fn;
+}
+
+int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box) {
+  sesa_encode_tiled_fn enc = sesa_get_encode_tiled();
+  if (enc == nullptr) {
+    sesa_set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return SESA_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sesa_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, stride0 %llu B)", (int)r,
+                   rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                   (unsigned long long)(rank > 1 ? strides_bytes[0] : 0));
+    return SESA_ERR_CUDA;
+  }
+  return SESA_OK;
+}
+
+extern "C" int64_t sesa_gemm_tc_table_bytes(int n_groups) { return (int64_t)sizeof(TcGroup) * (n_groups > 0 ? n_groups : 0); }
+
+extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int block_n, void* table_host,
+                                  int* total_tiles) {
+  SESA_CHECK_ARG(pr != nullptr && table_host != nullptr && total_tiles != nullptr, "sesa_gemm_tc_build: null argument");
+  SESA_CHECK_ARG(n_groups > 0 && n_groups <= MAX_GROUPS, "sesa_gemm_tc_build: group count %d out of range", n_groups);
+  SESA_CHECK_ARG(block_n == 128 || block_n == 256, "sesa_gemm_tc_build: block_n must be 128 or 256");
+  TcGroup* tab = reinterpret_cast<TcGroup*>(table_host);
+  int tiles = 0;
+  for (int i = 0; i < n_groups; ++i) {
+    const sesa_tc_problem& p = pr[i];
+    SESA_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0, "sesa_gemm_tc_build: empty problem %d", i);
+    SESA_CHECK_ARG((p.lda & 7) == 0 && (p.ldw & 7) == 0 && (p.a_plane & 7) == 0 && (p.w_plane & 7) == 0,
+                   "sesa_gemm_tc_build: problem %d: operand strides must be multiples of 8 bf16 elements", i);
+    SESA_CHECK_ARG((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0,
+                   "sesa_gemm_tc_build: problem %d: operands must be 16-byte aligned", i);
+    SESA_CHECK_ARG(p.lda >= p.K && p.ldw >= p.K, "sesa_gemm_tc_build: problem %d: row stride smaller than K", i);
+    TcGroup g;
+    memset(&g, 0, sizeof(g));
+    // The K extent is rounded up to the row stride where possible so that partial 64-wide slabs read the
+    // zero padding of the planes instead of relying on out-of-bounds fill alone (both give zeros).
+    const uint64_t dimsA[3] = {(uint64_t)p.K, (uint64_t)p.M, 2};
+    const uint64_t strA[2] = {(uint64_t)p.lda * 2, (uint64_t)(p.a_plane > 0 ? p.a_plane : p.lda * (int64_t)p.M) * 2};
+    const uint32_t boxA[3] = {BK, BM, 1};
+    int rc = sesa_make_tmap_bf16(&g.mapA, p.A, 3, dimsA, strA, boxA);
+    if (rc != SESA_OK) return rc;
+    const uint64_t dimsW[3] = {(uint64_t)p.K, (uint64_t)p.N, 2};
+    const uint64_t strW[2] = {(uint64_t)p.ldw * 2, (uint64_t)(p.w_plane > 0 ? p.w_plane : p.ldw * (int64_t)p.N) * 2};
+    const uint32_t boxW[3] = {BK, (uint32_t)block_n, 1};
+    rc = sesa_make_tmap_bf16(&g.mapW, p.W, 3, dimsW, strW, boxW);
+    if (rc != SESA_OK) return rc;
+    g.bias = p.bias;
+    g.rowscale = p.rowscale;
+    g.C = p.C;
+    g.P = reinterpret_cast<__nv_bfloat16*>(p.P);
+    g.ldc = p.ldc;
+    g.ldp = p.ldp;
+    g.p_plane = p.p_plane;
+    g.M = p.M;
+    g.N = p.N;
+    g.K = p.K;
+    g.n_blocks = (p.N + block_n - 1) / block_n;
+    g.k_blocks = (p.K + BK - 1) / BK;
+    g.tile_begin = tiles;
+    tiles += ((p.M + BM - 1) / BM) * g.n_blocks;
+    g.tile_end = tiles;
+    memcpy(&tab[i], &g, sizeof(g));
+  }
+  *total_tiles = tiles;
+  return SESA_OK;
+}
+
+extern "C" int sesa_gemm_tc(const void* table_dev, int n_groups, int total_tiles, int block_n, int nsplit,
+                            int out_planes, const sesa_gemm_epilogue* ep, void* stream) {
+  SESA_CHECK_ARG(table_dev != nullptr && ep != nullptr, "sesa_gemm_tc: null argument");
+  SESA_CHECK_ARG(n_groups > 0 && n_groups <= MAX_GROUPS, "sesa_gemm_tc: group count %d out of range", n_groups);
+  SESA_CHECK_ARG(nsplit == 1 || nsplit == 3, "sesa_gemm_tc: nsplit must be 1 or 3");
+  SESA_CHECK_ARG(out_planes == 1 || out_planes == 2, "sesa_gemm_tc: out_planes must be 1 or 2");
+  SESA_CHECK_ARG(ep->rot_cols == 0 || (ep->rot != nullptr && ep->rot_dim > 0 && (ep->rot_dim & 1) == 0 &&
+                                       (ep->rot_cols & 1) == 0 && ep->pos_div > 0 && ep->pos_mod > 0),
+                 "sesa_gemm_tc: bad rotary parameters");
+  SESA_CHECK_ARG(!(ep->glu && ep->residual), "sesa_gemm_tc: glu and residual are exclusive");
+  if (total_tiles <= 0) return SESA_OK;
+  const TcGroup* tab = reinterpret_cast<const TcGroup*>(table_dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (block_n == 256 && nsplit == 3) return launch_gemm_tc<256, 3>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  if (block_n == 256 && nsplit == 1) return launch_gemm_tc<256, 1>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  if (block_n == 128 && nsplit == 3) return launch_gemm_tc<128, 3>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  if (block_n == 128 && nsplit == 1) return launch_gemm_tc<128, 1>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  sesa_set_error("sesa_gemm_tc: unsupported block_n %d", block_n);
+  return SESA_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------ row prep
+// One warp per row: optional L2 normalisation, bf16 hi/lo planes, optional gate logits.
+__global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int dim,
+                                                        int normalize, __nv_bfloat16* __restrict__ planes, int64_t ldp,
+                                                        int64_t p_plane, int out_planes,
+                                                        const float* __restrict__ gate_w,
+                                                        const float* __restrict__ gate_b, int n_gates,
+                                                        float* __restrict__ gates, int64_t ldg,
+                                                        float* __restrict__ rowinv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  const int nv = dim >> 2;  // dim % 4 == 0 (checked by the host entry)
+  float inv = 1.0f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + 4 * i);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  if (rowinv != nullptr && lane == 0) rowinv[row] = inv;
+  float gacc[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) gacc[h] = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float4 v = *reinterpret_cast<const float4*>(xr + 4 * i);
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    if (planes != nullptr) {
+      __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+      tc::split_bf16(v.x, h0, l0); tc::split_bf16(v.y, h1, l1);
+      tc::split_bf16(v.z, h2, l2); tc::split_bf16(v.w, h3, l3);
+      __nv_bfloat16* pr = planes + row * ldp + 4 * i;
+      *reinterpret_cast<uint2*>(pr) = make_uint2(tc::pack_bf16(h0, h1), tc::pack_bf16(h2, h3));
+      if (out_planes > 1) *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(tc::pack_bf16(l0, l1), tc::pack_bf16(l2, l3));
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      if (h < n_gates) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(gate_w + (int64_t)h * dim + 4 * i));
+        gacc[h] += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+      }
+    }
+  }
+  if (n_gates > 0) {
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      if (h < n_gates) {
+        float a = gacc[h];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) gates[row * ldg + h] = a + (gate_b != nullptr ? gate_b[h] : 0.f);
+      }
+    }
+  }
+}
+
+extern "C" int sesa_prep_rows(const float* x, int64_t ldx, int64_t rows, int dim, int normalize, void* planes,
+                              int64_t ldp, int64_t p_plane, int out_planes, const float* gate_w, const float* gate_b,
+                              int n_gates, float* gates, int64_t ldg, float* rowinv, void* stream) {
+  SESA_CHECK_ARG(dim > 0 && (dim & 3) == 0 && (ldx & 3) == 0, "sesa_prep_rows: dim and ldx must be multiples of 4");
+  SESA_CHECK_ARG(planes == nullptr || ((ldp & 3) == 0 && (p_plane & 3) == 0), "sesa_prep_rows: plane strides must be multiples of 4");
+  SESA_CHECK_ARG(n_gates >= 0 && n_gates <= 8, "sesa_prep_rows: at most 8 gate outputs");
+  SESA_CHECK_ARG(n_gates == 0 || (gate_w != nullptr && gates != nullptr), "sesa_prep_rows: gates need weights and an output");
+  SESA_CHECK_ARG(out_planes == 1 || out_planes == 2, "sesa_prep_rows: out_planes must be 1 or 2");
+  if (rows <= 0) return SESA_OK;
+  const int wpb = 8;
+  prep_rows_kernel<<<(unsigned)ceil_div64(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      x, ldx, rows, dim, normalize, reinterpret_cast<__nv_bfloat16*>(planes), ldp, p_plane, out_planes, gate_w, gate_b,
+      n_gates, gates, ldg, rowinv);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+__global__ void split_weight_kernel(const float* __restrict__ w, int64_t rows, int64_t cols,
+                                    __nv_bfloat16* __restrict__ planes, int64_t ldp) {
+  const int64_t total = rows * ldp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ldp, c = i % ldp;
+    const float v = c < cols ? w[r * cols + c] : 0.f;
+    __nv_bfloat16 h, l;
+    tc::split_bf16(v, h, l);
+    planes[i] = h;
+    planes[total + i] = l;
+  }
+}
+
+extern "C" int sesa_split_weight(const float* w, int64_t rows, int64_t cols, void* planes, int64_t ldp, void* stream) {
+  SESA_CHECK_ARG(ldp >= cols && (ldp & 7) == 0, "sesa_split_weight: ldp must be a multiple of 8 and >= cols");
+  if (rows <= 0) return SESA_OK;
+  const int64_t total = rows * ldp;
+  split_weight_kernel<<<(unsigned)min((int64_t)2048, ceil_div64(total, 256)), 256, 0, (cudaStream_t)stream>>>(
+      w, rows, cols, reinterpret_cast<__nv_bfloat16*>(planes), ldp);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}

@@ -18,9 +18,11 @@ import math
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, tc
 from ._lib import GEMM_GROUP_DTYPE, GemmEpilogue, call
 from .module import KernelModule
+
+PRECISIONS = ('fp32', 'bf16', 'fp32_simt')
 
 DEFAULT_FREQS_PER_BANDS = (          # bs_roformer.py:315-324
     (2,) * 24 + (4,) * 12 + (12,) * 8 + (24,) * 8 + (48,) * 8 + (128, 129)
@@ -110,8 +112,8 @@ class _RoformerBase(KernelModule):
         self.dim_inputs = tuple(int(d) for d in dim_inputs)
         self.num_bands = len(self.dim_inputs)
         self.n_mask_linears = mask_estimator_depth + self.mask_extra_linear
-        self.precision = 'fp32'
-        self._ws = {}
+        self.precision = 'fp32'   # 'fp32': split-bf16 (3 MMAs) tensor-core path at fp32-parity tolerance;
+        self._ws = {}             # 'bf16': single bf16 MMA; 'fp32_simt': exact IEEE fp32 SIMT cross-check path
         g = torch.Generator().manual_seed(seed)
         D, inner, H = dim, self.inner, heads
         for i in range(depth):
@@ -147,6 +149,22 @@ class _RoformerBase(KernelModule):
                     self._register(p + 'weight', (dims[li + 1], dims[li]), 'linear_w', g)
                     self._register(p + 'bias', (dims[li + 1],), ('uniform', 1.0 / math.sqrt(dims[li])), g)
 
+    def set_precision(self, precision):
+        """'fp32' (default): tensor cores with split-bf16 operands (3 MMAs per product, fp32 accumulate) — meets the
+        fp32 parity gate; 'bf16': one bf16 MMA per product (SNR >= 40 dB gate); 'fp32_simt': exact IEEE fp32 SIMT
+        kernels (the in-library cross-check)."""
+        if precision not in PRECISIONS:
+            raise ValueError(f'precision must be one of {PRECISIONS}, got {precision!r}')
+        if precision != self.precision:
+            self.precision = precision
+            self._prepared = None
+            self._ws = {}
+        return self
+
+    @property
+    def _tc(self):
+        return self.precision != 'fp32_simt'
+
     # ------------------------------------------------------------------ weight preparation
     def _prepare(self):
         """Fold norms / scales into the GEMM weights and build the device-side constant tables."""
@@ -174,11 +192,16 @@ class _RoformerBase(KernelModule):
                     bias = torch.zeros(self.ld_qkv, device=dev)
                     bias[3 * inner:3 * inner + H] = P[p + '0.to_gates.bias']
                     g_ff = P[p + '1.net.0.gamma'] * sD
-                    subs.append(dict(
+                    sub = dict(
                         wqkv=w, bqkv=bias, wo=P[p + '0.to_out.0.weight'].contiguous(),
                         w1=(P[p + '1.net.1.weight'] * g_ff[None]).contiguous(), b1=P[p + '1.net.1.bias'].contiguous(),
                         w2=P[p + '1.net.4.weight'].contiguous(), b2=P[p + '1.net.4.bias'].contiguous(),
-                        freqs=P[p + '0.rotary_embed.freqs'].float().cpu()))
+                        freqs=P[p + '0.rotary_embed.freqs'].float().cpu())
+                    if self._tc:   # bf16 hi/lo planes of the folded weights for the tcgen05 GEMMs
+                        sub.update(wqkv_p=tc.split_weight(w[:3 * inner]), gate_w=w[3 * inner:3 * inner + H].contiguous(),
+                                   gate_b=bias[3 * inner:3 * inner + H].contiguous(), wo_p=tc.split_weight(sub['wo']),
+                                   w1_p=tc.split_weight(sub['w1']), w2_p=tc.split_weight(sub['w2']))
+                    subs.append(sub)
                 norm = P[f'layers.{i}.{a}.norm.gamma'].contiguous() if self.norm_output else None
                 pair.append(dict(subs=subs, norm=norm))
             prep['layers'].append(pair)
@@ -204,7 +227,8 @@ class _RoformerBase(KernelModule):
                     if li == self.n_mask_linears - 1:
                         w = torch.stack([w[:din], w[din:]], dim=1).reshape(2 * din, -1)
                         bias = torch.stack([bias[:din], bias[din:]], dim=1).reshape(2 * din)
-                    lins.append((w.contiguous(), bias.contiguous()))
+                    lins.append((w.contiguous(), bias.contiguous()) +
+                                ((tc.split_weight(w),) if self._tc else ()))
                 bands.append(lins)
             me.append(bands)
         prep['mask'] = me
@@ -271,7 +295,7 @@ class _RoformerBase(KernelModule):
             recs = []
             for n in range(self.num_stems):
                 for b, din in enumerate(self.dim_inputs):
-                    w, bias = prep['mask'][n][b][li]
+                    w, bias = prep['mask'][n][b][li][:2]
                     if li == 0:
                         A, lda = ws['x'].data_ptr() + 4 * b * D, nb * D
                     else:
@@ -302,8 +326,64 @@ class _RoformerBase(KernelModule):
                         ff2=single(ws['h'], s['w2'], s['b2'], ws['x'], M, D, 4 * D, 4 * D, D)))
                 gp.append(gs)
             ws['g_layers'].append(gp)
+        if self._tc:
+            self._workspace_tc(ws, prep, B, T)
         self._ws = {key: ws}   # keep one workspace alive
         return ws
+
+    def _workspace_tc(self, ws, prep, B, T):
+        """Plane buffers and TMA tables of the tensor-core path (built once per batch shape)."""
+        dev = self._device
+        nb, D, inner, M = self.num_bands, self.dim, self.inner, ws['M']
+        hidden = D * self.mlp_expansion_factor
+        BT = B * T
+        ws['xp'] = tc.alloc_planes(M, D, dev)          # normalised residual stream (A of qkv / ff1 / first mask Linear)
+        ws['aop'] = tc.alloc_planes(M, inner, dev)     # attention output (A of to_out)
+        ws['hp'] = tc.alloc_planes(M, 4 * D, dev)      # GELU(ff1) (A of ff2)
+        x, qkv = ws['x'], ws['qkv']
+
+        def one(A, Wp, Mm, N, K, bias=None, C=None, Pl=None):
+            return tc.TcGemmTable([dict(A=tc.planes_arg(A), W=tc.planes_arg(Wp), M=Mm, N=N, K=K,
+                                        bias=bias.data_ptr() if bias is not None else 0,
+                                        C=(C.data_ptr(), C.shape[-1]) if C is not None else None,
+                                        P=tc.planes_arg(Pl) if Pl is not None else None)], dev)
+        ws['t_layers'] = []
+        for pair in prep['layers']:
+            gp = []
+            for tr in pair:
+                gs = []
+                for s in tr['subs']:
+                    gs.append(dict(qkv=one(ws['xp'], s['wqkv_p'], M, 3 * inner, D, C=qkv),
+                                   out=one(ws['aop'], s['wo_p'], M, D, inner, C=x),
+                                   ff1=one(ws['xp'], s['w1_p'], M, 4 * D, D, bias=s['b1'], Pl=ws['hp']),
+                                   ff2=one(ws['hp'], s['w2_p'], M, D, 4 * D, bias=s['b2'], C=x)))
+                gp.append(gs)
+            ws['t_layers'].append(gp)
+        # mask estimators: grouped over (stem, band)
+        nl = self.n_mask_linears
+        ws['mhp'] = [torch.zeros(2, self.num_stems * nb * BT, hidden, device=dev, dtype=torch.bfloat16)
+                     for _ in range(min(2, nl - 1))]
+        offs = np.concatenate([[0], np.cumsum(self.dim_inputs)]).astype(np.int64)
+        xp = ws['xp']
+        ws['t_mask'] = []
+        for li in range(nl):
+            probs = []
+            for n in range(self.num_stems):
+                for b, din in enumerate(self.dim_inputs):
+                    w, bias, wp = prep['mask'][n][b][li]
+                    if li == 0:     # rows (b t) of band b inside the token-major stream: row stride nb*D
+                        A = (xp.data_ptr() + 2 * b * D, nb * D, xp.stride(0))
+                    else:
+                        src = ws['mhp'][(li - 1) % 2]
+                        A = (src.data_ptr() + 2 * (n * nb + b) * BT * hidden, hidden, src.stride(0))
+                    pr = dict(A=A, W=tc.planes_arg(wp), M=BT, N=w.shape[0], K=w.shape[1], bias=bias.data_ptr())
+                    if li == nl - 1:
+                        pr['C'] = (ws['mask'][n].data_ptr() + 4 * int(offs[b]), ws['ftot'])
+                    else:
+                        dst = ws['mhp'][li % 2]
+                        pr['P'] = (dst.data_ptr() + 2 * (n * nb + b) * BT * hidden, hidden, dst.stride(0))
+                    probs.append(pr)
+            ws['t_mask'].append(tc.TcGemmTable(probs, dev))
 
     def _features_buffer(self, ws, B, T):
         return ws['spec']
@@ -315,7 +395,7 @@ class _RoformerBase(KernelModule):
     def _gemm(self, table, ep):
         call('sesa_gemm_simt', _ptr(table.dev), table.n, table.max_m, table.max_n, ctypes.byref(ep), _stream())
 
-    def _transformer(self, ws, prep, gl, tr, axis, B):
+    def _transformer(self, ws, prep, gl, tr, axis, B, tgl=None):
         T, nb, D, H = ws['T'], self.num_bands, self.dim, self.heads
         M = ws['M']
         if axis == 0:   # time: sequences (b, f), positions t (row stride nb)
@@ -324,8 +404,25 @@ class _RoformerBase(KernelModule):
         else:           # band: sequences (b, t), positions f
             n_seq, seq_len, inner_cnt, outer, inner_s, pos_s = B * T, nb, 1, nb, 0, 1
             pos_div, pos_mod = 1, nb
-        for s, g in zip(tr['subs'], gl):
+        nsplit = 3 if self.precision == 'fp32' else 1
+        for si, (s, g) in enumerate(zip(tr['subs'], gl)):
             rot = self._rot_table(prep, s['freqs'], seq_len)
+            if self._tc:
+                t = tgl[si]
+                inner = self.inner
+                # RMSNorm (unit-norm rows; gamma*sqrt(D) lives in the weights) -> bf16 planes, + gate logits
+                tc.prep_rows(ws['x'], M, D, D, ws['xp'], True, s['gate_w'], s['gate_b'],
+                             ws['qkv'][:, 3 * inner:], self.ld_qkv)
+                t['qkv'].run(_epilogue(rot=rot, rot_cols=2 * inner, rot_dim=self.dim_head, pos_div=pos_div,
+                                       pos_mod=pos_mod), nsplit)
+                call('sesa_attention_simt', _ptr(ws['qkv']), _ptr(ws['ao']), self.ld_qkv, inner, H, self.dim_head,
+                     n_seq, seq_len, inner_cnt, outer, inner_s, pos_s, _stream())
+                tc.prep_rows(ws['ao'], M, inner, inner, ws['aop'], False)
+                t['out'].run(_epilogue(residual=1), nsplit)
+                tc.prep_rows(ws['x'], M, D, D, ws['xp'], True)
+                t['ff1'].run(_epilogue(act=_lib.ACT_GELU), nsplit)
+                t['ff2'].run(_epilogue(residual=1), nsplit)
+                continue
             self._gemm(g['qkv'], _epilogue(rownorm=1, rot=rot, rot_cols=2 * self.inner, rot_dim=self.dim_head,
                                            pos_div=pos_div, pos_mod=pos_mod))
             call('sesa_attention_simt', _ptr(ws['qkv']), _ptr(ws['ao']), self.ld_qkv, self.inner, H, self.dim_head,
@@ -360,13 +457,20 @@ class _RoformerBase(KernelModule):
             if self.skip_connection:
                 for j in range(i):
                     call('sesa_add_inplace', _ptr(ws['x']), _ptr(ws['store'][j]), ws['x'].numel(), st)
-            self._transformer(ws, prep, gp[0], pair[0], 0, B)
-            self._transformer(ws, prep, gp[1], pair[1], 1, B)
+            tgp = ws['t_layers'][i] if self._tc else (None, None)
+            self._transformer(ws, prep, gp[0], pair[0], 0, B, tgp[0])
+            self._transformer(ws, prep, gp[1], pair[1], 1, B, tgp[1])
             if self.skip_connection:
                 ws['store'][i].copy_(ws['x'])
         nl = self.n_mask_linears
+        if self._tc:
+            nsplit = 3 if self.precision == 'fp32' else 1
+            tc.prep_rows(ws['x'], ws['M'], self.dim, self.dim, ws['xp'], self.has_final_norm)
         for li in range(nl):
             last = li == nl - 1
+            if self._tc:
+                ws['t_mask'][li].run(_epilogue(act=0 if last else _lib.ACT_TANH, glu=1 if last else 0), nsplit)
+                continue
             self._gemm(ws['g_mask'][li], _epilogue(rownorm=1 if (li == 0 and self.has_final_norm) else 0,
                                                     act=0 if last else _lib.ACT_TANH, glu=1 if last else 0))
         out_len = ws['out_len']

@@ -1,0 +1,88 @@
+"""Host helpers of the tensor-core (tcgen05) kernels: bf16 hi/lo plane buffers and grouped-GEMM tables.
+
+A "plane pair" is a bf16 tensor of shape [2, rows, ld]: plane 0 = bf16(x), plane 1 = bf16(x - plane0).
+The tables hold the TMA tensor maps of sesa_gemm_tc (encoded on the host by the C library) and are
+built once per workspace; nothing here does arithmetic.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TC_PROBLEM_DTYPE, call
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round8(n):
+    return (int(n) + 7) // 8 * 8
+
+
+def alloc_planes(rows, cols, device, planes=2):
+    """bf16 [planes, rows, round8(cols)] zero-initialised (padding columns must stay zero)."""
+    return torch.zeros(planes, int(rows), round8(cols), device=device, dtype=torch.bfloat16)
+
+
+def split_weight(w):
+    """fp32 weight [N, K] on the device -> bf16 planes [2, N, round8(K)] (through the C library)."""
+    w = w.contiguous().float()
+    n, k = w.shape
+    out = torch.empty(2, n, round8(k), device=w.device, dtype=torch.bfloat16)
+    call('sesa_split_weight', _ptr(w), n, k, _ptr(out), round8(k), _stream())
+    return out
+
+
+def prep_rows(x, rows, dim, ldx, planes, normalize, gate_w=None, gate_b=None, gates=None, ldg=0, rowinv=None,
+              out_planes=2):
+    """x fp32 [rows, ldx] -> bf16 planes (+ gate logits, + inverse row norms)."""
+    n_gates = 0 if gate_w is None else int(gate_w.shape[0])
+    call('sesa_prep_rows', _ptr(x), ldx, rows, dim, 1 if normalize else 0,
+         _ptr(planes) if planes is not None else None,
+         planes.shape[-1] if planes is not None else 0,
+         planes.stride(0) if planes is not None else 0, out_planes,
+         _ptr(gate_w) if gate_w is not None else None, _ptr(gate_b) if gate_b is not None else None, n_gates,
+         _ptr(gates) if gates is not None else None, ldg, _ptr(rowinv) if rowinv is not None else None, _stream())
+
+
+class TcGemmTable:
+    """Device table of one (grouped) sesa_gemm_tc launch.
+
+    problems: list of dicts with keys A (bf16 planes tensor or (ptr, ld, plane_stride)), W (same), M, N, K and
+    optional bias, rowscale, C (ptr, ldc), P (ptr, ldp, plane_stride).
+    """
+
+    def __init__(self, problems, device, block_n=256):
+        n = len(problems)
+        arr = np.zeros(n, dtype=TC_PROBLEM_DTYPE)
+        for i, p in enumerate(problems):
+            a_ptr, lda, a_pl = p['A']
+            w_ptr, ldw, w_pl = p['W']
+            c_ptr, ldc = p.get('C') or (0, 0)
+            p_ptr, ldp, p_pl = p.get('P') or (0, 0, 0)
+            arr[i] = (a_ptr, w_ptr, p.get('bias') or 0, p.get('rowscale') or 0, c_ptr, p_ptr, lda, a_pl, ldw, w_pl,
+                      ldc, ldp, p_pl, p['M'], p['N'], p['K'], 0)
+        lib = _lib.load()
+        nbytes = int(lib.sesa_gemm_tc_table_bytes(n))
+        host = np.zeros(nbytes, dtype=np.uint8)
+        tiles = ctypes.c_int(0)
+        _lib.check(lib.sesa_gemm_tc_build(arr.ctypes.data_as(ctypes.c_void_p), n, block_n,
+                                          host.ctypes.data_as(ctypes.c_void_p), ctypes.byref(tiles)))
+        self.n, self.block_n, self.tiles = n, block_n, int(tiles.value)
+        self.dev = torch.from_numpy(host).to(device)
+        self.flops = sum(2 * int(p['M']) * int(p['N']) * int(p['K']) for p in problems)
+
+    def run(self, ep, nsplit=3, out_planes=2):
+        call('sesa_gemm_tc', _ptr(self.dev), self.n, self.tiles, self.block_n, nsplit, out_planes, ctypes.byref(ep),
+             _stream())
+
+
+def planes_arg(t, col_offset=0):
+    """(ptr, ld, plane_stride) of a [planes, rows, ld] bf16 tensor, optionally starting at a column."""
+    return (t.data_ptr() + 2 * int(col_offset), t.shape[-1], t.stride(0))

@@ -192,3 +192,147 @@ def test_rmsnorm_gather_add(lib):
     ref = a + b
     lib.call('sesa_add_inplace', P(a), P(b), 5000, S())
     assert torch.equal(a, ref)
+
+
+# ------------------------------------------------------------------ tensor-core (tcgen05) GEMM
+def _bf16_round(x):
+    return x.to(torch.bfloat16).to(torch.float64)
+
+
+def _tc_case(lib, M, N, K, nsplit, block_n, bias=True, act=0, rowscale=False, residual=False, glu=False, rot=None,
+             planes_out=False, seed=0):
+    from sesa_audio_separation_b200 import tc
+    from sesa_audio_separation_b200._lib import GemmEpilogue
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g) if bias else None
+    rs = (torch.rand(M, generator=g) + 0.5) if rowscale else None
+    ad, wd = a.to(dev), w.to(dev)
+    ap = tc.alloc_planes(M, K, dev)
+    assert K % 4 == 0
+    tc.prep_rows(ad, M, K, K, ap, normalize=False)
+    wp = tc.split_weight(wd)
+    n_out = N // 2 if glu else N
+    ldc = n_out + 4
+    c0 = torch.randn(M, ldc, generator=g)
+    cd = c0.to(dev).clone()
+    pout = tc.alloc_planes(M, n_out, dev) if planes_out else None
+    bd = b.to(dev) if bias else None
+    rsd = rs.to(dev) if rowscale else None
+    prob = dict(A=tc.planes_arg(ap), W=tc.planes_arg(wp), M=M, N=N, K=K, bias=bd.data_ptr() if bias else 0,
+                rowscale=rsd.data_ptr() if rowscale else 0, C=(cd.data_ptr(), ldc),
+                P=tc.planes_arg(pout) if planes_out else None)
+    tab = tc.TcGemmTable([prob], dev, block_n=block_n)
+    rot_d = None
+    ep = GemmEpilogue(0, act, 1 if residual else 0, 1 if glu else 0, 0, 0, 1, 1, None)
+    if rot is not None:
+        rot_cols, rot_dim, pos_div, pos_mod = rot
+        ang = torch.einsum('i,j->ij', torch.arange(pos_mod, dtype=torch.float32),
+                           1.0 / (10000 ** (torch.arange(0, rot_dim, 2).float() / rot_dim)))
+        rot_t = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+        rot_d = rot_t.to(dev)
+        ep = GemmEpilogue(0, act, 1 if residual else 0, 0, rot_cols, rot_dim, pos_div, pos_mod, rot_d.data_ptr())
+    tab.run(ep, nsplit=nsplit, out_planes=2)
+    torch.cuda.synchronize()
+    # reference in fp64 (operands rounded to bf16 in bf16 mode)
+    A64, W64 = a.double(), w.double()
+    if nsplit == 1:
+        A64, W64 = _bf16_round(a), _bf16_round(w)
+    y = A64 @ W64.T
+    if rowscale:
+        y = y * rs.double()[:, None]
+    if bias:
+        y = y + b.double()[None]
+    if act == 1:
+        y = torch.nn.functional.gelu(y)
+    elif act == 2:
+        y = y.tanh()
+    elif act == 3:
+        y = y.sigmoid()
+    if rot is not None:
+        pos = (torch.arange(M) // pos_div) % pos_mod
+        cs = rot_t.double()[pos]                                   # M, rot_dim/2, 2
+        yr = y[:, :rot_cols].reshape(M, rot_cols // rot_dim, rot_dim // 2, 2)
+        x1, x2 = yr[..., 0], yr[..., 1]
+        c, s = cs[:, None, :, 0], cs[:, None, :, 1]
+        y = torch.cat([torch.stack([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1).reshape(M, rot_cols), y[:, rot_cols:]], dim=1)
+    if glu:
+        y = y[:, 0::2] * y[:, 1::2].sigmoid()
+    if residual:
+        y = y + c0[:, :n_out].double()
+    got = cd.cpu()
+    assert torch.equal(got[:, n_out:], c0[:, n_out:]), 'wrote outside the output columns'
+    err = max_rel(y.numpy(), got[:, :n_out].numpy())
+    if planes_out:
+        pr = (pout[0].float() + pout[1].float()).cpu()[:, :n_out]
+        perr = max_rel(y.numpy(), pr.numpy())
+        assert perr < 5e-5, perr
+    return err
+
+
+@pytest.mark.parametrize('block_n', [256, 128])
+@pytest.mark.parametrize('nsplit', [3, 1])
+def test_gemm_tc_plain(lib, nsplit, block_n):
+    for (M, N, K) in [(128, 256, 64), (300, 512, 512), (1000, 1544, 512), (257, 2048, 128), (513, 512, 2048)]:
+        err = _tc_case(lib, M, N, K, nsplit, block_n, seed=M)
+        print('gemm_tc', M, N, K, nsplit, block_n, err)
+        assert err < (3e-5 if nsplit == 3 else 2e-5), (M, N, K, err)   # bf16 mode is compared with bf16-rounded operands
+
+
+def test_gemm_tc_ragged_and_epilogues(lib):
+    # ragged N / K tails (mask-estimator and band-split shapes), every epilogue
+    assert _tc_case(lib, 801, 16, 2048, 3, 256, act=0, glu=True) < 3e-5
+    assert _tc_case(lib, 801, 1032, 2048, 3, 256, glu=True, seed=3) < 3e-5
+    assert _tc_case(lib, 333, 96, 520, 3, 128, act=2, seed=4) < 3e-5
+    assert _tc_case(lib, 640, 2048, 512, 3, 256, act=1, rowscale=True, planes_out=True, seed=5) < 3e-5
+    assert _tc_case(lib, 640, 512, 2048, 3, 256, residual=True, planes_out=True, seed=6) < 3e-5
+    assert _tc_case(lib, 62 * 9, 1536, 512, 3, 256, bias=False, rot=(1024, 64, 62, 9), planes_out=True, seed=7) < 3e-5
+    assert _tc_case(lib, 200, 24, 8, 3, 256, seed=8) < 3e-5
+
+
+def test_gemm_tc_grouped(lib):
+    """62-band style grouped launch: different N per group, one launch."""
+    from sesa_audio_separation_b200 import tc
+    from sesa_audio_separation_b200._lib import GemmEpilogue
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(11)
+    M, K = 500, 256
+    Ns = [16, 48, 512, 520, 96, 1032]
+    a = [torch.randn(M, K, generator=g) for _ in Ns]
+    w = [torch.randn(n, K, generator=g) / 16 for n in Ns]
+    keep, probs, outs = [], [], []
+    for ai, wi, n in zip(a, w, Ns):
+        ap = tc.alloc_planes(M, K, dev)
+        ad = ai.to(dev)
+        tc.prep_rows(ad, M, K, K, ap, normalize=False)
+        wp = tc.split_weight(wi.to(dev))
+        c = torch.zeros(M, n, device=dev)
+        keep += [ap, ad, wp]
+        outs.append(c)
+        probs.append(dict(A=tc.planes_arg(ap), W=tc.planes_arg(wp), M=M, N=n, K=K, C=(c.data_ptr(), n)))
+    tab = tc.TcGemmTable(probs, dev)
+    tab.run(GemmEpilogue(0, 0, 0, 0, 0, 0, 1, 1, None), nsplit=3)
+    torch.cuda.synchronize()
+    for ai, wi, c in zip(a, w, outs):
+        assert max_rel((ai.double() @ wi.double().T).numpy(), c.cpu().numpy()) < 3e-5
+
+
+def test_prep_rows(lib):
+    from sesa_audio_separation_b200 import tc
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(12)
+    M, D, H = 777, 512, 8
+    x = torch.randn(M, D, generator=g) * 3
+    gw, gb = torch.randn(H, D, generator=g) / 20, torch.randn(H, generator=g)
+    xd, gwd, gbd = x.to(dev), gw.to(dev), gb.to(dev)
+    planes = tc.alloc_planes(M, D, dev)
+    gates = torch.zeros(M, 12, device=dev)
+    inv = torch.zeros(M, device=dev)
+    tc.prep_rows(xd, M, D, D, planes, True, gwd, gbd, gates, 12, inv)
+    xn = torch.nn.functional.normalize(x.double(), dim=-1)
+    rec = (planes[0].float() + planes[1].float()).cpu().double()
+    assert max_rel(xn.numpy(), rec.numpy()) < 1e-5
+    assert max_rel((xn @ gw.double().T + gb.double()).numpy(), gates[:, :H].cpu().numpy()) < 1e-5
+    assert max_rel((1 / x.double().norm(dim=-1)).numpy(), inv.cpu().numpy()) < 1e-6
