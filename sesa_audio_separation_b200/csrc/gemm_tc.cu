@@ -20,9 +20,12 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;           // one 128-byte swizzle row of bf16
+constexpr int BK = 64;            // one 128-byte swizzle row of bf16
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int EPI_WARPS = 8;      // two per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_COLS = 16;      // accumulator columns per epilogue step
+constexpr int EPI_STAGE_BYTES = 32 * EPI_COLS * 4;  // per-warp transpose buffer (2 KB)
 constexpr int MAX_GROUPS = 1024;
 
 struct alignas(128) TcGroup {
@@ -44,16 +47,35 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;               // 16 KB per plane
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + MAX_GROUPS * 4;
+  static constexpr int STAGES = (196 * 1024) / STAGE_BYTES >= 6 ? 6 : (196 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int TILE_OFF = BAR_OFF + 256;
+  static constexpr int SMEM_BYTES = TILE_OFF + MAX_GROUPS * 4 + 1024 /*alignment slack*/;
   static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: power of two
 };
 
-__device__ __forceinline__ float act_apply_tc(float v, int act) {
-  if (act == SESA_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-  if (act == SESA_ACT_TANH) return tanhf(v);
-  if (act == SESA_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
-  return v;
+// erf with < 1 ulp error, branch-free (both ranges evaluated, then selected) so that the unrolled epilogue
+// stays compact and divergence-free.
+__device__ __forceinline__ float erf_fast(float a) {
+  const float t = fabsf(a);
+  const float s = a * a;
+  float r = fmaf(-1.72853470e-5f, t, 3.83197126e-4f);
+  const float u = fmaf(-3.88396438e-3f, t, 2.42546219e-2f);
+  r = fmaf(r, s, u);
+  r = fmaf(r, t, -1.06777877e-1f);
+  r = fmaf(r, t, -6.34846687e-1f);
+  r = fmaf(r, t, -1.28717512e-1f);
+  r = fmaf(r, t, -t);
+  const float big = copysignf(1.0f - exp2f(r * 1.4426950408889634f), a);
+  float p = -5.96761703e-4f;
+  p = fmaf(p, s, 4.99119423e-3f);
+  p = fmaf(p, s, -2.67681349e-2f);
+  p = fmaf(p, s, 1.12819925e-1f);
+  p = fmaf(p, s, -3.76125336e-1f);
+  p = fmaf(p, s, 1.28379166e-1f);
+  const float small = fmaf(p, a, a);
+  return t > 0.927734375f ? big : small;
 }
 
 __device__ __forceinline__ int find_group(const int* tile_end, int n_groups, int tile) {
@@ -62,7 +84,22 @@ __device__ __forceinline__ int find_group(const int* tile_end, int n_groups, int
   return g;
 }
 
-template <int BN, int NSPLIT>
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Epilogue flavours are compile-time so that each kernel's epilogue loop stays small enough for the
+// instruction cache (one epilogue warp per scheduler cannot hide instruction-fetch misses).
+enum { F_PLAIN = 0, F_ROT = 1, F_GELU = 2, F_TANH = 3, F_GLU = 4, F_GENERIC = 5 };
+
+template <int BN, int NSPLIT, int FLAVOR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles, sesa_gemm_epilogue ep,
                int out_planes) {
@@ -70,13 +107,13 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* full_bar = bars;                      // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;         // [STAGES]
   uint64_t* tmem_full = bars + 2 * C::STAGES;     // [2]
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-  int* tile_end = reinterpret_cast<int*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+  int* tile_end = reinterpret_cast<int*>(smem + C::TILE_OFF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,7 +126,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(&tmem_full[a], 1);
-      tc::mbar_init(&tmem_empty[a], 4);
+      tc::mbar_init(&tmem_empty[a], EPI_WARPS);
     }
     tc::fence_barrier_init();
   }
@@ -165,7 +202,14 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     }
   } else {
     // ================= epilogue warps =================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // Phase A (thread = accumulator row): TMEM -> registers, scale / bias / activation / rotary.
+    // Phase B (after a conflict-free transpose through shared memory): 4 lanes cover one row's 16 columns, so
+    // the residual read, the fp32 store and the bf16 plane stores are all sector-complete and coalesced.
+    const int ew = warp - 2;
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int ch = ew >> 2;          // which half of the tile's columns
+    constexpr int HALF = BN / 2;
+    float* stage = reinterpret_cast<float*>(smem + C::EPI_OFF + ew * EPI_STAGE_BYTES);
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -173,111 +217,161 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       const int t = tile - g->tile_begin;
       const int mb = t / g->n_blocks, nb = t % g->n_blocks;
       const int M = g->M, N = g->N;
-      const int m = mb * BM + q * 32 + lane;
+      const int m_base = mb * BM + q * 32;
+      const int m = m_base + lane;
       const bool row_ok = m < M;
-      const int n0 = nb * BN;
-      const float* bias = g->bias;
-      float* Cp = g->C;
-      __nv_bfloat16* Pp = g->P;
+      const int n_half = nb * BN + ch * HALF;
+      const float* __restrict__ bias = g->bias;
+      float* __restrict__ Cp = g->C;
+      __nv_bfloat16* __restrict__ Pp = g->P;
       const int64_t ldc = g->ldc, ldp = g->ldp, p_plane = g->p_plane;
       const float rs = (g->rowscale != nullptr && row_ok) ? g->rowscale[m] : 1.0f;
       int pos = 0;
-      if (ep.rot_cols > 0) pos = (m / ep.pos_div) % ep.pos_mod;
-      const bool c_vec = Cp != nullptr && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15) == 0;
-      const bool p_vec = Pp != nullptr && (ldp & 7) == 0 && (p_plane & 7) == 0 && (reinterpret_cast<uintptr_t>(Pp) & 15) == 0;
+      if ((FLAVOR == F_ROT || FLAVOR == F_GENERIC) && ep.rot_cols > 0) pos = (m / ep.pos_div) % ep.pos_mod;
+      const bool c_vec = Cp == nullptr || ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
+      const bool p_vec = Pp == nullptr || ((ldp & 3) == 0 && (p_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(Pp) & 7) == 0);
+      constexpr bool kGeneric = FLAVOR == F_GENERIC;
+      const bool use_glu = FLAVOR == F_GLU || (kGeneric && ep.glu);
+      const int act = FLAVOR == F_GELU ? SESA_ACT_GELU : FLAVOR == F_TANH ? SESA_ACT_TANH : kGeneric ? ep.act : SESA_ACT_NONE;
+      const int rot_cols = (FLAVOR == F_ROT || kGeneric) ? ep.rot_cols : 0;
+      const bool staged = c_vec && p_vec && !use_glu;
+      // this lane's slice of the bias for the warp's column half (columns n_half + 4*lane ..)
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias != nullptr && lane * 4 < HALF) {
+        const int bc = n_half + lane * 4;
+        if (bc + 3 < N && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
+          b4 = __ldg(reinterpret_cast<const float4*>(bias + bc));
+        } else {
+          if (bc < N) b4.x = bias[bc];
+          if (bc + 1 < N) b4.y = bias[bc + 1];
+          if (bc + 2 < N) b4.z = bias[bc + 2];
+          if (bc + 3 < N) b4.w = bias[bc + 3];
+        }
+      }
 
       tc::mbar_wait(&tmem_full[as], aph);
       tc::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + ch * HALF;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n = n0 + c * 32;
+      for (int c = 0; c < HALF / EPI_COLS; ++c) {
+        const int n = n_half + c * EPI_COLS;
         if (n >= N) break;  // warp-uniform
-        float v[32];
-        tc::tmem_ld32(t_row + c * 32, v);
+        // phase-B coordinates of this lane: rows it*8 + lane/4, columns n + 4*(lane%4) ..
+        const int c4 = lane & 3;
+        const int colb = n + c4 * 4;
+        float4 res[4];
+        if (staged && ep.residual) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int mm = m_base + it * 8 + (lane >> 2);
+            res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mm < M && colb + 3 < N) res[it] = *reinterpret_cast<const float4*>(Cp + (int64_t)mm * ldc + colb);
+          }
+        }
+        float4 rt4[4];
+        const bool do_rot = n < rot_cols;
+        if (do_rot) {
+          const float4* rp = reinterpret_cast<const float4*>(ep.rot) +
+                             (((int64_t)pos * (ep.rot_dim >> 1) + ((n % ep.rot_dim) >> 1)) >> 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rt4[i] = __ldg(rp + i);
+        }
+        float v[EPI_COLS];
+        tmem_ld16(t_row + c * EPI_COLS, v);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = v[j] * rs;
-          if (bias != nullptr && n + j < N) x += __ldg(bias + n + j);
-          v[j] = act_apply_tc(x, ep.act);
+        for (int j = 0; j < EPI_COLS; ++j) {
+          const int src = c * 4 + (j >> 2);
+          const float bsel = (j & 3) == 0 ? b4.x : (j & 3) == 1 ? b4.y : (j & 3) == 2 ? b4.z : b4.w;
+          v[j] = fmaf(v[j], rs, __shfl_sync(0xffffffffu, bsel, src));
         }
-        if (n < ep.rot_cols) {
-          const int half = ep.rot_dim >> 1;
-          const float2* rt = reinterpret_cast<const float2*>(ep.rot) + (int64_t)pos * half;
+        if (act == SESA_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            if (n + j < ep.rot_cols) {
-              const float2 cs = __ldg(rt + (((n + j) % ep.rot_dim) >> 1));
-              const float x1 = v[j], x2 = v[j + 1];
-              v[j] = x1 * cs.x - x2 * cs.y;
-              v[j + 1] = x2 * cs.x + x1 * cs.y;
-            }
+          for (int j = 0; j < EPI_COLS; ++j) v[j] = 0.5f * v[j] * (1.0f + erf_fast(v[j] * 0.70710678118654752440f));
+        } else if (act == SESA_ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < EPI_COLS; ++j) v[j] = tanhf(v[j]);
+        } else if (act == SESA_ACT_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < EPI_COLS; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+        }
+        if (do_rot) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x1 = v[4 * i], x2 = v[4 * i + 1], x3 = v[4 * i + 2], x4 = v[4 * i + 3];
+            v[4 * i] = x1 * rt4[i].x - x2 * rt4[i].y;
+            v[4 * i + 1] = x2 * rt4[i].x + x1 * rt4[i].y;
+            v[4 * i + 2] = x3 * rt4[i].z - x4 * rt4[i].w;
+            v[4 * i + 3] = x4 * rt4[i].z + x3 * rt4[i].w;
           }
         }
-        int width = 32, nbase = n, nlimit = N;
-        if (ep.glu) {  // rows of W interleaved (value, gate): out[:, n/2 + j] = v[2j] * sigmoid(v[2j+1])
+        if (staged) {
+          // transpose through shared memory; 16-byte blocks XOR-swizzled by (row>>1)&3: both phases conflict-free
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * (1.0f / (1.0f + expf(-v[2 * j + 1])));
-          width = 16;
-          nbase = n >> 1;
-          nlimit = N >> 1;
-        }
-        if (row_ok) {
-          const bool full = nbase + width <= nlimit;
-          if (Cp != nullptr) {
-            float* crow = Cp + (int64_t)m * ldc + nbase;
-            if (c_vec && full && (nbase & 3) == 0) {
+          for (int j4 = 0; j4 < 4; ++j4)
+            *reinterpret_cast<float4*>(stage + lane * EPI_COLS + ((j4 ^ ((lane >> 1) & 3)) << 2)) =
+                make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (j < width) {
-                  float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                  if (ep.residual) {
-                    const float4 r = *reinterpret_cast<const float4*>(crow + j);
-                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                    v[j] = o.x; v[j + 1] = o.y; v[j + 2] = o.z; v[j + 3] = o.w;  // planes carry the new stream
-                  }
-                  *reinterpret_cast<float4*>(crow + j) = o;
-                }
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2);
+            const int mm = m_base + r;
+            float4 o = *reinterpret_cast<const float4*>(stage + r * EPI_COLS + ((c4 ^ ((r >> 1) & 3)) << 2));
+            if (mm >= M || colb >= N) continue;
+            if (colb + 3 < N) {
+              if (ep.residual) { o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w; }
+              if (Cp != nullptr) *reinterpret_cast<float4*>(Cp + (int64_t)mm * ldc + colb) = o;
+              if (Pp != nullptr) {
+                __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+                tc::split_bf16(o.x, h0, l0); tc::split_bf16(o.y, h1, l1);
+                tc::split_bf16(o.z, h2, l2); tc::split_bf16(o.w, h3, l3);
+                __nv_bfloat16* pr = Pp + (int64_t)mm * ldp + colb;
+                *reinterpret_cast<uint2*>(pr) = make_uint2(tc::pack_bf16(h0, h1), tc::pack_bf16(h2, h3));
+                if (out_planes > 1) *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(tc::pack_bf16(l0, l1), tc::pack_bf16(l2, l3));
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j < width && nbase + j < nlimit) {
-                  if (ep.residual) v[j] += crow[j];
-                  crow[j] = v[j];
+            } else {  // ragged right edge of the problem
+              const float ov[4] = {o.x, o.y, o.z, o.w};
+              for (int e = 0; e < 4 && colb + e < N; ++e) {
+                float val = ov[e];
+                if (Cp != nullptr) {
+                  float* cp = Cp + (int64_t)mm * ldc + colb + e;
+                  if (ep.residual) val += *cp;
+                  *cp = val;
                 }
-              }
-            }
-          }
-          if (Pp != nullptr) {
-            __nv_bfloat16* prow = Pp + (int64_t)m * ldp + nbase;
-            if (p_vec && full && (nbase & 7) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (j < width) {
-                  uint32_t hi[4], lo[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    tc::split_bf16(v[j + 2 * e], h0, l0);
-                    tc::split_bf16(v[j + 2 * e + 1], h1, l1);
-                    hi[e] = tc::pack_bf16(h0, h1);
-                    lo[e] = tc::pack_bf16(l0, l1);
-                  }
-                  *reinterpret_cast<uint4*>(prow + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                  if (out_planes > 1) *reinterpret_cast<uint4*>(prow + p_plane + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j < width && nbase + j < nlimit) {
+                if (Pp != nullptr) {
                   __nv_bfloat16 h, l;
-                  tc::split_bf16(v[j], h, l);
-                  prow[j] = h;
-                  if (out_planes > 1) prow[p_plane + j] = l;
+                  tc::split_bf16(val, h, l);
+                  Pp[(int64_t)mm * ldp + colb + e] = h;
+                  if (out_planes > 1) Pp[(int64_t)mm * ldp + p_plane + colb + e] = l;
                 }
+              }
+            }
+          }
+          __syncwarp();
+        } else if (row_ok) {
+          // generic path (GLU or unaligned outputs): each thread writes its own row
+          int width = EPI_COLS, nbase = n, nlimit = N;
+          if (use_glu) {  // rows of W interleaved (value, gate): out[:, n/2 + j] = v[2j] * sigmoid(v[2j+1])
+#pragma unroll
+            for (int j = 0; j < EPI_COLS / 2; ++j) v[j] = v[2 * j] * (1.0f / (1.0f + expf(-v[2 * j + 1])));
+            width = EPI_COLS / 2;
+            nbase = n >> 1;
+            nlimit = N >> 1;
+          }
+#pragma unroll
+          for (int j = 0; j < EPI_COLS; ++j) {
+            if (j < width && nbase + j < nlimit) {
+              float val = v[j];
+              if (Cp != nullptr) {
+                float* cp = Cp + (int64_t)m * ldc + nbase + j;
+                if (ep.residual) val += *cp;
+                *cp = val;
+              }
+              if (Pp != nullptr) {
+                __nv_bfloat16 h, l;
+                tc::split_bf16(val, h, l);
+                Pp[(int64_t)m * ldp + nbase + j] = h;
+                if (out_planes > 1) Pp[(int64_t)m * ldp + p_plane + nbase + j] = l;
               }
             }
           }
@@ -295,23 +389,47 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
   if (warp == 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int BN, int NSPLIT>
-int launch_gemm_tc(const TcGroup* table, int n_groups, int total_tiles, const sesa_gemm_epilogue& ep, int out_planes,
-                   cudaStream_t stream) {
+template <int BN, int NSPLIT, int FLAVOR>
+int launch_gemm_tc_f(const TcGroup* table, int n_groups, int total_tiles, const sesa_gemm_epilogue& ep, int out_planes,
+                     cudaStream_t stream) {
   using C = Cfg<BN, NSPLIT>;
   static_assert(C::STAGES >= 2, "pipeline needs at least two stages");
   static bool configured = false;
   if (!configured) {
-    SESA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SESA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, NSPLIT, FLAVOR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   C::SMEM_BYTES));
     configured = true;
   }
-  int dev = 0, sms = 0;
-  SESA_CUDA(cudaGetDevice(&dev));
-  SESA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    SESA_CUDA(cudaGetDevice(&dev));
+    SESA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   const int grid = total_tiles < sms ? total_tiles : sms;
-  gemm_tc_kernel<BN, NSPLIT><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(table, n_groups, total_tiles, ep, out_planes);
+  gemm_tc_kernel<BN, NSPLIT, FLAVOR><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(table, n_groups, total_tiles, ep,
+                                                                                   out_planes);
   SESA_LAUNCH_CHECK();
   return SESA_OK;
+}
+
+template <int BN, int NSPLIT>
+int launch_gemm_tc(const TcGroup* table, int n_groups, int total_tiles, const sesa_gemm_epilogue& ep, int out_planes,
+                   cudaStream_t stream) {
+  int flavor = F_GENERIC;
+  if (ep.glu && ep.act == SESA_ACT_NONE && ep.rot_cols == 0) flavor = F_GLU;
+  else if (!ep.glu && ep.rot_cols > 0 && ep.act == SESA_ACT_NONE) flavor = F_ROT;
+  else if (!ep.glu && ep.rot_cols == 0 && ep.act == SESA_ACT_NONE) flavor = F_PLAIN;
+  else if (!ep.glu && ep.rot_cols == 0 && ep.act == SESA_ACT_GELU) flavor = F_GELU;
+  else if (!ep.glu && ep.rot_cols == 0 && ep.act == SESA_ACT_TANH) flavor = F_TANH;
+  switch (flavor) {
+    case F_PLAIN: return launch_gemm_tc_f<BN, NSPLIT, F_PLAIN>(table, n_groups, total_tiles, ep, out_planes, stream);
+    case F_ROT: return launch_gemm_tc_f<BN, NSPLIT, F_ROT>(table, n_groups, total_tiles, ep, out_planes, stream);
+    case F_GELU: return launch_gemm_tc_f<BN, NSPLIT, F_GELU>(table, n_groups, total_tiles, ep, out_planes, stream);
+    case F_TANH: return launch_gemm_tc_f<BN, NSPLIT, F_TANH>(table, n_groups, total_tiles, ep, out_planes, stream);
+    case F_GLU: return launch_gemm_tc_f<BN, NSPLIT, F_GLU>(table, n_groups, total_tiles, ep, out_planes, stream);
+    default: return launch_gemm_tc_f<BN, NSPLIT, F_GENERIC>(table, n_groups, total_tiles, ep, out_planes, stream);
+  }
 }
 
 }  // namespace
@@ -415,9 +533,10 @@ extern "C" int sesa_gemm_tc(const void* table_dev, int n_groups, int total_tiles
   SESA_CHECK_ARG(n_groups > 0 && n_groups <= MAX_GROUPS, "sesa_gemm_tc: group count %d out of range", n_groups);
   SESA_CHECK_ARG(nsplit == 1 || nsplit == 3, "sesa_gemm_tc: nsplit must be 1 or 3");
   SESA_CHECK_ARG(out_planes == 1 || out_planes == 2, "sesa_gemm_tc: out_planes must be 1 or 2");
-  SESA_CHECK_ARG(ep->rot_cols == 0 || (ep->rot != nullptr && ep->rot_dim > 0 && (ep->rot_dim & 1) == 0 &&
-                                       (ep->rot_cols & 1) == 0 && ep->pos_div > 0 && ep->pos_mod > 0),
-                 "sesa_gemm_tc: bad rotary parameters");
+  SESA_CHECK_ARG(ep->rot_cols == 0 || (ep->rot != nullptr && ep->rot_dim > 0 && (ep->rot_dim & 15) == 0 &&
+                                       (ep->rot_cols & 15) == 0 && ep->pos_div > 0 && ep->pos_mod > 0 &&
+                                       (reinterpret_cast<uintptr_t>(ep->rot) & 15) == 0),
+                 "sesa_gemm_tc: bad rotary parameters (rot_cols and rot_dim must be multiples of 16)");
   SESA_CHECK_ARG(!(ep->glu && ep->residual), "sesa_gemm_tc: glu and residual are exclusive");
   if (total_tiles <= 0) return SESA_OK;
   const TcGroup* tab = reinterpret_cast<const TcGroup*>(table_dev);
