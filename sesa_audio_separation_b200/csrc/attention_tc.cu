@@ -1,0 +1,377 @@
+// Flash-style attention on the Blackwell tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// Replaces Attend.forward (models/bs_roformer/attend.py:89-93,113-126: softmax(q k^T) v, no mask, non-causal)
+// together with the sigmoid gating and head merge of Attention.forward (models/bs_roformer/bs_roformer.py:115-120).
+// q/k/v arrive as bf16 hi/lo planes written by the to_qkv GEMM epilogue (q pre-scaled by dh^-0.5, q and k already
+// rotated); the gated output leaves as bf16 hi/lo planes, i.e. directly as the A operand of the to_out GEMM.
+//
+// The residual stream is token-major [(b t f), d], so the axial "rearranges" of bs_roformer.py:526-543 are TMA
+// tensor-map strides: a time sequence (b, f) is a strided walk over t, a band sequence (b, t) is contiguous.
+//   STRIDED mode: one sequence per CTA tile: 128 query rows x KV blocks of 64 keys (time attention, seq 801).
+//   PACKED  mode: short contiguous sequences (seq_len <= 64) are packed floor(128/seq_len) per 128-row tile with a
+//                 block-diagonal mask (band attention, seq 62 -> 2 sequences per tile).
+// Per KV block: S = Q K^T (UMMA 128x64x64) -> TMEM; the 128 softmax threads (thread = row) read S, do the online
+// softmax in fp32, write P as bf16 hi/lo into 128B-swizzled shared memory; O_blk = P V (UMMA 128x64x64, V as the
+// MN-major operand) -> TMEM; threads fold O_blk into their fp32 running output.  fp32 parity uses the same
+// three-product split as the GEMM (hi.hi + hi.lo + lo.hi).  Two CTAs are resident per SM so one CTA's softmax
+// overlaps the other's MMAs.
+#include "common.cuh"
+#include "sesa_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int DH = 64;
+constexpr int BQ = 128;
+constexpr int BKV = 64;
+constexpr int ATT_THREADS = 160;  // warps 0-3: softmax / accumulate (thread = query row); warp 4: TMA + MMA issue
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnParams {
+  const float* gates;   // [rows][ldg] gate logits
+  __nv_bfloat16* out;   // [planes][rows][ldo]
+  int64_t ldg, ldo, out_plane;
+  int heads, inner;     // inner = heads * DH: k at column inner + h*DH, v at 2*inner + h*DH
+  int mode;             // 0 strided, 1 packed
+  int seq_len, n_seq;
+  int inner_cnt;        // strided: sequence s -> (b = s / inner_cnt, f = s % inner_cnt)
+  int64_t outer_stride, inner_stride, pos_stride;  // strided: row = b*outer + f*inner + pos*pos_stride
+  int spt;              // packed: sequences per tile
+  int out_planes;
+};
+
+template <int NSPLIT>
+struct ACfg {
+  static constexpr int NP = NSPLIT == 3 ? 2 : 1;
+  static constexpr int Q_BYTES = BQ * 128;    // one plane of the Q tile (128 rows x 64 bf16)
+  static constexpr int KV_BYTES = BKV * 128;  // one plane of a K or V block
+  static constexpr int P_BYTES = BQ * 128;    // one plane of P (128 rows x 64 keys)
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + NP * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + NP * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + NP * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + NP * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
+  using C = ACfg<NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem + C::OFF_Q;
+  uint8_t* sK = smem + C::OFF_K;
+  uint8_t* sV = smem + C::OFF_V;
+  uint8_t* sP = smem + C::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* s_full = bars + 3;
+  uint64_t* p_full = bars + 4;
+  uint64_t* o_full = bars + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int h = blockIdx.z;
+
+  if (tid == 128) {
+    tc::mbar_init(q_full, 1);
+    tc::mbar_init(k_full, 1);
+    tc::mbar_init(v_full, 1);
+    tc::mbar_init(s_full, 1);
+    tc::mbar_init(p_full, 128);
+    tc::mbar_init(o_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 4) {
+    tc::tmem_alloc(tmem_ptr, 128);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base;        // columns [0, 64)
+  const uint32_t tmem_O = tmem_base + 64;   // columns [64, 128)
+
+  // ---- work item geometry
+  int nblk, q0 = 0;
+  int c1 = 0, c3 = 0;          // TMA coordinates that stay fixed (strided: f and b)
+  int64_t row_base = 0;        // packed: first row of the tile
+  if (p.mode == 0) {
+    const int seq = blockIdx.y;
+    q0 = blockIdx.x * BQ;
+    c1 = seq % p.inner_cnt;
+    c3 = seq / p.inner_cnt;
+    nblk = (p.seq_len + BKV - 1) / BKV;
+  } else {
+    row_base = (int64_t)blockIdx.x * p.spt * p.seq_len;
+    nblk = BQ / BKV;
+  }
+
+  if (warp == 4) {
+    // ================= control warp: TMA loads + MMA issue =================
+    if (tc::elect_one()) {
+      auto load_rows = [&](uint8_t* dst, uint64_t* bar, int col, int r0, int plane) {
+        // 64 rows x 64 columns of one plane
+        if (p.mode == 0) tc::tma_load_5d(dst, &map, bar, col, c1, r0, c3, plane);
+        else tc::tma_load_5d(dst, &map, bar, col, (int)(row_base + r0), 0, 0, plane);   // rows beyond the tensor: zero fill
+      };
+      const int colq = h * DH, colk = p.inner + h * DH, colv = 2 * p.inner + h * DH;
+      tc::mbar_expect_tx(q_full, C::NP * C::Q_BYTES);
+#pragma unroll
+      for (int pl = 0; pl < C::NP; ++pl) {
+        load_rows(sQ + pl * C::Q_BYTES, q_full, colq, q0, pl);
+        load_rows(sQ + pl * C::Q_BYTES + C::KV_BYTES, q_full, colq, q0 + 64, pl);
+      }
+      tc::mbar_expect_tx(k_full, C::NP * C::KV_BYTES);
+#pragma unroll
+      for (int pl = 0; pl < C::NP; ++pl) load_rows(sK + pl * C::KV_BYTES, k_full, colk, 0, pl);
+      tc::mbar_expect_tx(v_full, C::NP * C::KV_BYTES);
+#pragma unroll
+      for (int pl = 0; pl < C::NP; ++pl) load_rows(sV + pl * C::KV_BYTES, v_full, colv, 0, pl);
+
+      constexpr uint32_t idesc_s = tc::make_idesc_bf16(BQ, BKV, 0, 0);  // S = Q K^T : both K-major
+      constexpr uint32_t idesc_o = tc::make_idesc_bf16(BQ, DH, 0, 1);   // O = P V   : V is MN-major
+      const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
+      auto issue_s = [&]() {
+#pragma unroll
+        for (int prod = 0; prod < NSPLIT; ++prod) {
+          const uint32_t qa = aQ + (prod == 2 ? C::Q_BYTES : 0);
+          const uint32_t ka = aK + (prod == 1 ? C::KV_BYTES : 0);
+#pragma unroll
+          for (int ks = 0; ks < DH / 16; ++ks)
+            tc::umma_f16(tmem_S, tc::make_smem_desc_sw128(qa + ks * 32), tc::make_smem_desc_sw128(ka + ks * 32), idesc_s,
+                         (prod | ks) != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(s_full);
+      };
+      auto issue_o = [&]() {
+#pragma unroll
+        for (int prod = 0; prod < NSPLIT; ++prod) {
+          const uint32_t pa = aP + (prod == 2 ? C::P_BYTES : 0);
+          const uint32_t va = aV + (prod == 1 ? C::KV_BYTES : 0);
+#pragma unroll
+          for (int ks = 0; ks < BKV / 16; ++ks)
+            tc::umma_f16(tmem_O, tc::make_smem_desc_sw128(pa + ks * 32), tc::make_smem_desc_sw128(va + ks * 2048, 8192),
+                         idesc_o, (prod | ks) != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(o_full);
+      };
+
+      tc::mbar_wait(q_full, 0);
+      tc::mbar_wait(k_full, 0);
+      tc::tc_fence_after();
+      issue_s();
+      for (int j = 0; j < nblk; ++j) {
+        const uint32_t ph = j & 1;
+        const bool more = j + 1 < nblk;
+        tc::mbar_wait(s_full, ph);   // S_j retired: the K buffer is free
+        if (more) {
+          tc::mbar_expect_tx(k_full, C::NP * C::KV_BYTES);
+#pragma unroll
+          for (int pl = 0; pl < C::NP; ++pl) load_rows(sK + pl * C::KV_BYTES, k_full, colk, (j + 1) * BKV, pl);
+        }
+        tc::mbar_wait(p_full, ph);   // P_j is in shared memory (and S_j has been read out of TMEM)
+        tc::mbar_wait(v_full, ph);
+        tc::tc_fence_after();
+        issue_o();
+        if (more) {
+          tc::mbar_wait(k_full, ph ^ 1);
+          tc::tc_fence_after();
+          issue_s();                 // queued behind P_j V_j on the tensor pipe; overlaps the accumulate of block j
+        }
+        tc::mbar_wait(o_full, ph);   // P_j V_j retired: V and P buffers are free
+        if (more) {
+          tc::mbar_expect_tx(v_full, C::NP * C::KV_BYTES);
+#pragma unroll
+          for (int pl = 0; pl < C::NP; ++pl) load_rows(sV + pl * C::KV_BYTES, v_full, colv, (j + 1) * BKV, pl);
+        }
+      }
+    }
+  } else {
+    // ================= softmax / accumulate threads: thread = query row =================
+    const int i = tid;  // row of the tile == TMEM lane
+    int lo = 0, hi = p.seq_len;         // valid key range (tile-relative key index)
+    bool row_valid;
+    int64_t out_row;
+    if (p.mode == 0) {
+      row_valid = q0 + i < p.seq_len;
+      out_row = (int64_t)c3 * p.outer_stride + (int64_t)c1 * p.inner_stride + (int64_t)(q0 + i) * p.pos_stride;
+    } else {
+      const int sl = i / p.seq_len;
+      const int64_t gseq = (int64_t)blockIdx.x * p.spt + sl;
+      row_valid = sl < p.spt && gseq < p.n_seq;
+      lo = row_valid ? sl * p.seq_len : 0;
+      hi = row_valid ? lo + p.seq_len : 0;
+      out_row = row_base + i;
+    }
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
+    float mrun = -INFINITY, lrun = 0.f;
+    uint8_t* prow_hi = sP + i * 128;
+    const int sw = i & 7;
+
+    for (int j = 0; j < nblk; ++j) {
+      const uint32_t ph = j & 1;
+      tc::mbar_wait(s_full, ph);
+      tc::tc_fence_after();
+      float s[BKV];
+      tc::tmem_ld32(tmem_S + lane_off, s);
+      tc::tmem_ld32(tmem_S + lane_off + 32, s + 32);
+      tc::tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BKV; ++c) {
+        const int kj = j * BKV + c;
+        s[c] = (kj >= lo && kj < hi) ? s[c] * LOG2E : -INFINITY;
+        mx = fmaxf(mx, s[c]);
+      }
+      const float mnew = fmaxf(mrun, mx);
+      const float moff = mnew == -INFINITY ? 0.f : mnew;
+      const float corr = exp2f(mrun - moff);
+      float sum = 0.f;
+#pragma unroll
+      for (int c8 = 0; c8 < BKV / 8; ++c8) {
+        uint32_t ph_[4], pl_[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = exp2f(s[c8 * 8 + 2 * e] - moff);
+          const float p1 = exp2f(s[c8 * 8 + 2 * e + 1] - moff);
+          sum += p0 + p1;
+          __nv_bfloat16 h0, l0, h1, l1;
+          tc::split_bf16(p0, h0, l0);
+          tc::split_bf16(p1, h1, l1);
+          ph_[e] = tc::pack_bf16(h0, h1);
+          pl_[e] = tc::pack_bf16(l0, l1);
+        }
+        const int off = ((c8 ^ sw) << 4);
+        *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
+        if (NSPLIT == 3) *reinterpret_cast<uint4*>(prow_hi + C::P_BYTES + off) = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
+      }
+      lrun = lrun * corr + sum;
+      mrun = mnew;
+      tc::fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      tc::tc_fence_before();
+      tc::mbar_arrive(p_full);
+
+      tc::mbar_wait(o_full, ph);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float ob[32];
+        tc::tmem_ld32(tmem_O + lane_off + half * 32, ob);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 32; ++d) o[half * 32 + d] = fmaf(o[half * 32 + d], corr, ob[d]);
+      }
+      tc::tc_fence_before();
+    }
+
+    if (row_valid) {
+      const float gl = p.gates[out_row * p.ldg + h];
+      const float sc = (1.0f / (1.0f + expf(-gl))) / lrun;
+      __nv_bfloat16* op = p.out + out_row * p.ldo + h * DH;
+#pragma unroll
+      for (int d8 = 0; d8 < DH / 8; ++d8) {
+        uint32_t hh[4], ll[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          tc::split_bf16(o[d8 * 8 + 2 * e] * sc, h0, l0);
+          tc::split_bf16(o[d8 * 8 + 2 * e + 1] * sc, h1, l1);
+          hh[e] = tc::pack_bf16(h0, h1);
+          ll[e] = tc::pack_bf16(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(op + d8 * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        if (p.out_planes > 1) *reinterpret_cast<uint4*>(op + p.out_plane + d8 * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem_base, 128);
+}
+
+template <int NSPLIT>
+int launch_attention_tc(const CUtensorMap& map, const AttnParams& p, dim3 grid, cudaStream_t stream) {
+  using C = ACfg<NSPLIT>;
+  static bool configured = false;
+  if (!configured) {
+    SESA_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  attention_tc_kernel<NSPLIT><<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(map, p);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+}  // namespace
+
+extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t plane_stride, const float* gates,
+                                 int64_t ldg, void* out_planes_ptr, int64_t ldo, int64_t out_plane_stride, int heads,
+                                 int dim_head, int n_seq, int seq_len, int inner_cnt, int64_t outer_stride,
+                                 int64_t inner_stride, int64_t pos_stride, int nsplit, int out_planes, void* stream) {
+  SESA_CHECK_ARG(dim_head == DH, "sesa_attention_tc: dim_head must be 64, got %d", dim_head);
+  SESA_CHECK_ARG((ld & 7) == 0 && (ldo & 7) == 0 && (plane_stride & 7) == 0 && (out_plane_stride & 7) == 0,
+                 "sesa_attention_tc: plane strides must be multiples of 8 bf16 elements");
+  SESA_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_planes_ptr) & 15) == 0,
+                 "sesa_attention_tc: plane buffers must be 16-byte aligned");
+  SESA_CHECK_ARG(inner_cnt > 0 && seq_len > 0 && heads > 0, "sesa_attention_tc: bad sequence geometry");
+  SESA_CHECK_ARG(nsplit == 1 || nsplit == 3, "sesa_attention_tc: nsplit must be 1 or 3");
+  SESA_CHECK_ARG(out_planes == 1 || out_planes == 2, "sesa_attention_tc: out_planes must be 1 or 2");
+  if (n_seq == 0) return SESA_OK;
+  const int inner = heads * DH;
+  AttnParams p;
+  p.gates = gates;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out_planes_ptr);
+  p.ldg = ldg;
+  p.ldo = ldo;
+  p.out_plane = out_plane_stride;
+  p.heads = heads;
+  p.inner = inner;
+  p.seq_len = seq_len;
+  p.n_seq = n_seq;
+  p.inner_cnt = inner_cnt;
+  p.outer_stride = outer_stride;
+  p.inner_stride = inner_stride;
+  p.pos_stride = pos_stride;
+  p.out_planes = out_planes;
+  p.spt = 1;
+  CUtensorMap map;
+  dim3 grid;
+  const bool packed = pos_stride == 1 && seq_len <= BKV && inner_cnt == 1 && outer_stride == seq_len;
+  const uint32_t box[5] = {64, 1, 64, 1, 1};
+  if (packed) {
+    // rows are one contiguous run of n_seq*seq_len tokens
+    p.mode = 1;
+    p.spt = BQ / seq_len;
+    const uint64_t rows = (uint64_t)n_seq * seq_len;
+    const uint64_t dims[5] = {(uint64_t)3 * inner, rows, 1, 1, 2};
+    const uint64_t str[4] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * rows, (uint64_t)ld * 2 * rows, (uint64_t)plane_stride * 2};
+    const uint32_t boxp[5] = {64, 64, 1, 1, 1};
+    int rc = sesa_make_tmap_bf16(&map, qkv_planes, 5, dims, str, boxp);
+    if (rc != SESA_OK) return rc;
+    grid = dim3((unsigned)((n_seq + p.spt - 1) / p.spt), 1, heads);
+  } else {
+    // sequence s = (b, f): row = b*outer + f*inner + pos*pos_stride
+    p.mode = 0;
+    const int n_outer = n_seq / inner_cnt;
+    SESA_CHECK_ARG(n_outer * inner_cnt == n_seq, "sesa_attention_tc: n_seq must be a multiple of inner_cnt");
+    const uint64_t dims[5] = {(uint64_t)3 * inner, (uint64_t)inner_cnt, (uint64_t)seq_len, (uint64_t)n_outer, 2};
+    const uint64_t str[4] = {(uint64_t)(inner_cnt > 1 ? inner_stride : 1) * ld * 2, (uint64_t)pos_stride * ld * 2,
+                             (uint64_t)outer_stride * ld * 2, (uint64_t)plane_stride * 2};
+    int rc = sesa_make_tmap_bf16(&map, qkv_planes, 5, dims, str, box);
+    if (rc != SESA_OK) return rc;
+    SESA_CHECK_ARG(n_seq <= 65535, "sesa_attention_tc: too many sequences for one launch (%d)", n_seq);
+    grid = dim3((unsigned)((seq_len + BQ - 1) / BQ), (unsigned)n_seq, heads);
+  }
+  if (nsplit == 3) return launch_attention_tc<3>(map, p, grid, (cudaStream_t)stream);
+  return launch_attention_tc<1>(map, p, grid, (cudaStream_t)stream);
+}

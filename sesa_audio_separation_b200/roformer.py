@@ -340,7 +340,9 @@ class _RoformerBase(KernelModule):
         ws['xp'] = tc.alloc_planes(M, D, dev)          # normalised residual stream (A of qkv / ff1 / first mask Linear)
         ws['aop'] = tc.alloc_planes(M, inner, dev)     # attention output (A of to_out)
         ws['hp'] = tc.alloc_planes(M, 4 * D, dev)      # GELU(ff1) (A of ff2)
-        x, qkv = ws['x'], ws['qkv']
+        ws['qkvp'] = tc.alloc_planes(M, 3 * inner, dev)  # rotated q (pre-scaled) | rotated k | v
+        ws['gates'] = torch.zeros(M, 8, device=dev, dtype=torch.float32)   # to_gates logits
+        x = ws['x']
 
         def one(A, Wp, Mm, N, K, bias=None, C=None, Pl=None):
             return tc.TcGemmTable([dict(A=tc.planes_arg(A), W=tc.planes_arg(Wp), M=Mm, N=N, K=K,
@@ -353,7 +355,7 @@ class _RoformerBase(KernelModule):
             for tr in pair:
                 gs = []
                 for s in tr['subs']:
-                    gs.append(dict(qkv=one(ws['xp'], s['wqkv_p'], M, 3 * inner, D, C=qkv),
+                    gs.append(dict(qkv=one(ws['xp'], s['wqkv_p'], M, 3 * inner, D, Pl=ws['qkvp']),
                                    out=one(ws['aop'], s['wo_p'], M, D, inner, C=x),
                                    ff1=one(ws['xp'], s['w1_p'], M, 4 * D, D, bias=s['b1'], Pl=ws['hp']),
                                    ff2=one(ws['hp'], s['w2_p'], M, D, 4 * D, bias=s['b2'], C=x)))
@@ -411,13 +413,13 @@ class _RoformerBase(KernelModule):
                 t = tgl[si]
                 inner = self.inner
                 # RMSNorm (unit-norm rows; gamma*sqrt(D) lives in the weights) -> bf16 planes, + gate logits
-                tc.prep_rows(ws['x'], M, D, D, ws['xp'], True, s['gate_w'], s['gate_b'],
-                             ws['qkv'][:, 3 * inner:], self.ld_qkv)
+                tc.prep_rows(ws['x'], M, D, D, ws['xp'], True, s['gate_w'], s['gate_b'], ws['gates'], 8)
                 t['qkv'].run(_epilogue(rot=rot, rot_cols=2 * inner, rot_dim=self.dim_head, pos_div=pos_div,
                                        pos_mod=pos_mod), nsplit)
-                call('sesa_attention_simt', _ptr(ws['qkv']), _ptr(ws['ao']), self.ld_qkv, inner, H, self.dim_head,
-                     n_seq, seq_len, inner_cnt, outer, inner_s, pos_s, _stream())
-                tc.prep_rows(ws['ao'], M, inner, inner, ws['aop'], False)
+                qp, ap = ws['qkvp'], ws['aop']
+                call('sesa_attention_tc', _ptr(qp), qp.shape[-1], qp.stride(0), _ptr(ws['gates']), 8, _ptr(ap),
+                     ap.shape[-1], ap.stride(0), H, self.dim_head, n_seq, seq_len, inner_cnt, outer, inner_s, pos_s,
+                     nsplit, 2, _stream())
                 t['out'].run(_epilogue(residual=1), nsplit)
                 tc.prep_rows(ws['x'], M, D, D, ws['xp'], True)
                 t['ff1'].run(_epilogue(act=_lib.ACT_GELU), nsplit)

@@ -336,3 +336,46 @@ def test_prep_rows(lib):
     assert max_rel(xn.numpy(), rec.numpy()) < 1e-5
     assert max_rel((xn @ gw.double().T + gb.double()).numpy(), gates[:, :H].cpu().numpy()) < 1e-5
     assert max_rel((1 / x.double().norm(dim=-1)).numpy(), inv.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize('nsplit', [3, 1])
+@pytest.mark.parametrize('axis,B,T,F', [(0, 2, 150, 20), (1, 2, 150, 20), (0, 1, 801, 3), (1, 3, 33, 62), (1, 1, 5, 60),
+                                        (1, 2, 7, 100), (0, 1, 64, 2)])
+def test_attention_tc(lib, axis, B, T, F, nsplit):
+    from sesa_audio_separation_b200 import tc
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(5)
+    H, dh = 3, 64
+    inner = H * dh
+    M = B * T * F
+    qkv = torch.randn(M, 3 * inner, generator=g)
+    qkv[:, :inner] *= 0.35
+    gl = torch.randn(M, 8, generator=g)
+    qd, gd = qkv.to(dev), gl.to(dev)
+    planes = tc.alloc_planes(M, 3 * inner, dev)
+    tc.prep_rows(qd, M, 3 * inner, 3 * inner, planes, False)
+    out = tc.alloc_planes(M, inner, dev)
+    if axis == 0:
+        args = (B * F, T, F, T * F, 1, F)
+    else:
+        args = (B * T, F, 1, F, 0, 1)
+    lib.call('sesa_attention_tc', P(planes), planes.shape[-1], planes.stride(0), P(gd), 8, P(out), out.shape[-1],
+             out.stride(0), H, dh, *args, nsplit, 2, S())
+    torch.cuda.synchronize()
+    src = qkv if nsplit == 3 else planes[0].float().cpu()
+    x = src.reshape(B, T, F, 3 * inner).double()
+    q = x[..., :inner].reshape(B, T, F, H, dh)
+    k = x[..., inner:2 * inner].reshape(B, T, F, H, dh)
+    v = x[..., 2 * inner:].reshape(B, T, F, H, dh)
+    gate = gl[:, :H].double().sigmoid().reshape(B, T, F, H)
+    if axis == 0:
+        sim = torch.einsum('bifhd,bjfhd->bfhij', q, k)
+        o = torch.einsum('bfhij,bjfhd->bifhd', sim.softmax(-1), v)
+    else:
+        sim = torch.einsum('btihd,btjhd->bthij', q, k)
+        o = torch.einsum('bthij,btjhd->btihd', sim.softmax(-1), v)
+    ref = (o * gate[..., None]).reshape(M, inner)
+    got = (out[0].float() + out[1].float()).cpu()
+    err = max_rel(ref.numpy(), got.numpy())
+    print('attention_tc axis', axis, (B, T, F), 'nsplit', nsplit, 'max_rel', err)
+    assert err < (3e-5 if nsplit == 3 else 1e-2)
