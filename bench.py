@@ -134,7 +134,7 @@ def main():
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
-    ap.add_argument('--precision', default='fp32')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16', 'fp32_simt'])
     ap.add_argument('--seconds', type=float, default=180.0)
     ap.add_argument('--engine-batch', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -230,23 +230,42 @@ def main():
         n_chunks = eng.plan.n_chunks
         gemm_f, att_f = flops_per_chunk(MODEL_CFG, CHUNK)
         tf_peak, hbm_peak, peak_src = peaks()
-        gemm_n, gemm_ms = prof.get('gemm', (0, 0.0))
+        tc_mode = args.precision != 'fp32_simt'
+        gemm_cls = 'gemm_tc' if tc_mode else 'gemm_simt'
+        gemm_n, gemm_ms = prof.get(gemm_cls, (0, 0.0))
         breakdown = {k: {'launches': n, 'ms': round(t, 3)} for k, (n, t) in sorted(prof.items())}
-        achieved = (gemm_f * n_chunks / 1e12) / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
+        # the tensor-core class runs every GEMM except the (tiny) band-split Linears
+        fpb = (2,) * 24 + (4,) * 12 + (12,) * 8 + (24,) * 8 + (48,) * 8 + (128, 129)
+        band_f = 2 * (1 + CHUNK // MODEL_CFG['stft_hop_length']) * sum(4 * f for f in fpb) * MODEL_CFG['dim']
+        cls_f = gemm_f - band_f if tc_mode else gemm_f
+        achieved = (cls_f * n_chunks / 1e12) / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
+        mma_mult = 3 if args.precision == 'fp32' else 1
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_gemm_tc_traffic.json')
+        if tc_mode and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get('dram_bytes_per_launch_avg')
         line = {
             'metric': 'seconds of audio separated per second (x realtime), BS-RoFormer vocals',
             'value': audio_s / (ms_total / 1e3), 'unit': 'x realtime', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32' if args.precision == 'fp32' else args.precision, 'data': 'synthetic',
+            'dtype': {'fp32': 'bf16x3 (split-bf16 tensor-core products, fp32 accumulate: fp32-parity mode)',
+                      'bf16': 'bf16 (fp32 accumulate)', 'fp32_simt': 'f32'}[args.precision], 'data': 'synthetic',
             'config': dict(base_cfg, engine_batch=args.engine_batch, precision=args.precision),
             'e2e': {'value': audio_s / float(t_e2e.item()), 'unit': 'x realtime',
                     'h2d_bytes_per_step': int(mix_host.numel() * 4), 'd2h_bytes_per_step': int(out_bytes)},
             'gpu_launches': int(launches), 'clocks': clocks,
-            'roofline': {'kernel': 'GEMM class (qkv/out/ff + band-split + mask-estimator launches)', 'bound': 'tensor',
+            'roofline': {'kernel': ('gemm_tc_kernel<256,NSPLIT,flavour> (tcgen05 grouped GEMM: to_qkv / to_out / FeedForward / '
+                                    'MaskEstimator launches)') if tc_mode else 'gemm_simt_kernel', 'bound': 'tensor',
                          'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf_peak,
-                         'traffic': None, 'peak_source': peak_src, 'launches_per_step': gemm_n,
-                         'algorithmic_tflop_per_chunk': gemm_f / 1e12, 'share_of_step': gemm_ms / max(1e-9, sum(t for _, t in prof.values()))},
+                         'traffic': traffic, 'peak_source': peak_src, 'launches_per_step': gemm_n,
+                         'algorithmic_tflop_per_chunk': cls_f / 1e12,
+                         'mma_tflops_issued': achieved * mma_mult,
+                         'mma_frac_of_peak': achieved * mma_mult / tf_peak,
+                         'note': ('fp32-parity mode issues 3 bf16 MMAs per algorithmic product (hi.hi + hi.lo + lo.hi), so '
+                                  'frac (algorithmic) is bounded by 1/3; mma_frac_of_peak is the tensor-pipe view')
+                                 if mma_mult == 3 else '',
+                         'share_of_step': gemm_ms / max(1e-9, sum(t for _, t in prof.values()))},
             'breakdown_ms_per_step': breakdown, 'attention_tflop_per_chunk': att_f / 1e12,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -66,6 +66,9 @@ _SIGS = {
     'sesa_overlap_add': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int,
                                  c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                  c_void_p]),
+    'sesa_overlap_add_range': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64,
+                                       c_int, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64,
+                                       c_int, c_int64, c_int64, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -102,7 +105,7 @@ LAUNCHES = 0
 _profile = None   # dict: class -> [ (start_event, end_event), ... ] when enabled
 _CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_attention_simt': 'attention',
           'sesa_attention_tc': 'attention', 'sesa_stft': 'stft', 'sesa_mask_istft': 'mask_istft',
-          'sesa_overlap_add': 'overlap_add', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}
+          'sesa_overlap_add': 'overlap_add', 'sesa_overlap_add_range': 'overlap_add', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}
 
 
 def profile_start():

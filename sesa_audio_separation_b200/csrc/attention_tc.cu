@@ -11,8 +11,8 @@
 //   PACKED  mode: short contiguous sequences (seq_len <= 64) are packed floor(128/seq_len) per 128-row tile with a
 //                 block-diagonal mask (band attention, seq 62 -> 2 sequences per tile).
 // Per KV block: S = Q K^T (UMMA 128x64x64) -> TMEM; the 128 softmax threads (thread = row) read S, do the online
-// softmax in fp32, write P as bf16 hi/lo into 128B-swizzled shared memory; O_blk = P V (UMMA 128x64x64, V as the
-// MN-major operand) -> TMEM; threads fold O_blk into their fp32 running output.  fp32 parity uses the same
+// softmax in fp32, write P as packed bf16 hi/lo back into TENSOR MEMORY (tcgen05.st); O_blk = P V (UMMA 128x64x64 with
+// A read from TMEM and V as the MN-major shared-memory operand, K/V blocks double-buffered by TMA) -> TMEM; threads fold O_blk into their fp32 running output.  fp32 parity uses the same
 // three-product split as the GEMM (hi.hi + hi.lo + lo.hi).  Two CTAs are resident per SM so one CTA's softmax
 // overlaps the other's MMAs.
 #include "common.cuh"
@@ -24,7 +24,8 @@ namespace {
 constexpr int DH = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 64;
-constexpr int ATT_THREADS = 160;  // warps 0-3: softmax / accumulate (thread = query row); warp 4: TMA + MMA issue
+constexpr int SM_THREADS = 256;   // warps 0-7: softmax / accumulate; thread (row = (warp&3)*32+lane, half = warp>>2)
+constexpr int ATT_THREADS = SM_THREADS + 32;  // warp 8: TMA + MMA issue
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnParams {
@@ -45,13 +46,15 @@ struct ACfg {
   static constexpr int NP = NSPLIT == 3 ? 2 : 1;
   static constexpr int Q_BYTES = BQ * 128;    // one plane of the Q tile (128 rows x 64 bf16)
   static constexpr int KV_BYTES = BKV * 128;  // one plane of a K or V block
-  static constexpr int P_BYTES = BQ * 128;    // one plane of P (128 rows x 64 keys)
+  static constexpr int KV_STAGES = 2;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NP * Q_BYTES;
-  static constexpr int OFF_V = OFF_K + NP * KV_BYTES;
-  static constexpr int OFF_P = OFF_V + NP * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_P + NP * P_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_STAGES * NP * KV_BYTES;
+  static constexpr int OFF_X = OFF_V + KV_STAGES * NP * KV_BYTES;   // float xch[2][2][128]: row max / row sum exchange
+  static constexpr int OFF_BAR = OFF_X + 2 * 2 * BQ * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  // TMEM columns: S fp32 [0,64) | O fp32 [64,128) | P bf16x2: hi [128,160), lo [160,192)
+  static constexpr int TMEM_COLS = 256;
 };
 
 template <int NSPLIT>
@@ -63,39 +66,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
   uint8_t* sQ = smem + C::OFF_Q;
   uint8_t* sK = smem + C::OFF_K;
   uint8_t* sV = smem + C::OFF_V;
-  uint8_t* sP = smem + C::OFF_P;
+  float* xch = reinterpret_cast<float*>(smem + C::OFF_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* v_full = bars + 2;
-  uint64_t* s_full = bars + 3;
-  uint64_t* p_full = bars + 4;
-  uint64_t* o_full = bars + 5;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* v_full = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int h = blockIdx.z;
 
-  if (tid == 128) {
+  if (tid == SM_THREADS) {
     tc::mbar_init(q_full, 1);
-    tc::mbar_init(k_full, 1);
-    tc::mbar_init(v_full, 1);
+    tc::mbar_init(&k_full[0], 1);
+    tc::mbar_init(&k_full[1], 1);
+    tc::mbar_init(&v_full[0], 1);
+    tc::mbar_init(&v_full[1], 1);
     tc::mbar_init(s_full, 1);
-    tc::mbar_init(p_full, 128);
+    tc::mbar_init(p_full, SM_THREADS);
     tc::mbar_init(o_full, 1);
     tc::fence_barrier_init();
   }
-  if (warp == 4) {
-    tc::tmem_alloc(tmem_ptr, 128);
+  if (warp == 8) {
+    tc::tmem_alloc(tmem_ptr, C::TMEM_COLS);
     tc::tmem_relinquish();
   }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S = tmem_base;        // columns [0, 64)
-  const uint32_t tmem_O = tmem_base + 64;   // columns [64, 128)
+  const uint32_t tmem_S = tmem_base;         // fp32 scores, columns [0, 64)
+  const uint32_t tmem_O = tmem_base + 64;    // fp32 block output, columns [64, 128)
+  const uint32_t tmem_P = tmem_base + 128;   // bf16 pairs: hi plane [128,160), lo plane [160,192)
 
   // ---- work item geometry
   int nblk, q0 = 0;
@@ -112,36 +118,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
     nblk = BQ / BKV;
   }
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ================= control warp: TMA loads + MMA issue =================
     if (tc::elect_one()) {
       auto load_rows = [&](uint8_t* dst, uint64_t* bar, int col, int r0, int plane) {
-        // 64 rows x 64 columns of one plane
+        // 64 rows x 64 columns of one plane (rows beyond the tensor are zero-filled by TMA)
         if (p.mode == 0) tc::tma_load_5d(dst, &map, bar, col, c1, r0, c3, plane);
-        else tc::tma_load_5d(dst, &map, bar, col, (int)(row_base + r0), 0, 0, plane);   // rows beyond the tensor: zero fill
+        else tc::tma_load_5d(dst, &map, bar, col, (int)(row_base + r0), 0, 0, plane);
       };
       const int colq = h * DH, colk = p.inner + h * DH, colv = 2 * p.inner + h * DH;
+      auto load_k = [&](int j) {
+        const int st = j & 1;
+        tc::mbar_expect_tx(&k_full[st], C::NP * C::KV_BYTES);
+#pragma unroll
+        for (int pl = 0; pl < C::NP; ++pl) load_rows(sK + (st * C::NP + pl) * C::KV_BYTES, &k_full[st], colk, j * BKV, pl);
+      };
+      auto load_v = [&](int j) {
+        const int st = j & 1;
+        tc::mbar_expect_tx(&v_full[st], C::NP * C::KV_BYTES);
+#pragma unroll
+        for (int pl = 0; pl < C::NP; ++pl) load_rows(sV + (st * C::NP + pl) * C::KV_BYTES, &v_full[st], colv, j * BKV, pl);
+      };
       tc::mbar_expect_tx(q_full, C::NP * C::Q_BYTES);
 #pragma unroll
       for (int pl = 0; pl < C::NP; ++pl) {
         load_rows(sQ + pl * C::Q_BYTES, q_full, colq, q0, pl);
         load_rows(sQ + pl * C::Q_BYTES + C::KV_BYTES, q_full, colq, q0 + 64, pl);
       }
-      tc::mbar_expect_tx(k_full, C::NP * C::KV_BYTES);
-#pragma unroll
-      for (int pl = 0; pl < C::NP; ++pl) load_rows(sK + pl * C::KV_BYTES, k_full, colk, 0, pl);
-      tc::mbar_expect_tx(v_full, C::NP * C::KV_BYTES);
-#pragma unroll
-      for (int pl = 0; pl < C::NP; ++pl) load_rows(sV + pl * C::KV_BYTES, v_full, colv, 0, pl);
+      load_k(0);
+      load_v(0);
+      if (nblk > 1) {
+        load_k(1);
+        load_v(1);
+      }
 
       constexpr uint32_t idesc_s = tc::make_idesc_bf16(BQ, BKV, 0, 0);  // S = Q K^T : both K-major
-      constexpr uint32_t idesc_o = tc::make_idesc_bf16(BQ, DH, 0, 1);   // O = P V   : V is MN-major
-      const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV), aP = tc::smem_u32(sP);
-      auto issue_s = [&]() {
+      constexpr uint32_t idesc_o = tc::make_idesc_bf16(BQ, DH, 0, 1);   // O = P V   : P from TMEM, V MN-major
+      const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
+      auto issue_s = [&](int st) {
 #pragma unroll
         for (int prod = 0; prod < NSPLIT; ++prod) {
           const uint32_t qa = aQ + (prod == 2 ? C::Q_BYTES : 0);
-          const uint32_t ka = aK + (prod == 1 ? C::KV_BYTES : 0);
+          const uint32_t ka = aK + (st * C::NP + (prod == 1 ? 1 : 0)) * C::KV_BYTES;
 #pragma unroll
           for (int ks = 0; ks < DH / 16; ++ks)
             tc::umma_f16(tmem_S, tc::make_smem_desc_sw128(qa + ks * 32), tc::make_smem_desc_sw128(ka + ks * 32), idesc_s,
@@ -149,53 +167,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
         }
         tc::umma_commit(s_full);
       };
-      auto issue_o = [&]() {
+      auto issue_o = [&](int st) {
 #pragma unroll
         for (int prod = 0; prod < NSPLIT; ++prod) {
-          const uint32_t pa = aP + (prod == 2 ? C::P_BYTES : 0);
-          const uint32_t va = aV + (prod == 1 ? C::KV_BYTES : 0);
+          const uint32_t pa = tmem_P + (prod == 2 ? 32 : 0);
+          const uint32_t va = aV + (st * C::NP + (prod == 1 ? 1 : 0)) * C::KV_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < BKV / 16; ++ks)
-            tc::umma_f16(tmem_O, tc::make_smem_desc_sw128(pa + ks * 32), tc::make_smem_desc_sw128(va + ks * 2048, 8192),
-                         idesc_o, (prod | ks) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < BKV / 16; ++ks)   // 16 keys = 8 packed TMEM columns of P, 16 rows (2 KB) of V
+            tc::umma_f16_ts(tmem_O, pa + ks * 8, tc::make_smem_desc_sw128(va + ks * 2048, 8192), idesc_o,
+                            (prod | ks) != 0 ? 1u : 0u);
         }
         tc::umma_commit(o_full);
       };
 
       tc::mbar_wait(q_full, 0);
-      tc::mbar_wait(k_full, 0);
+      tc::mbar_wait(&k_full[0], 0);
       tc::tc_fence_after();
-      issue_s();
+      issue_s(0);
       for (int j = 0; j < nblk; ++j) {
         const uint32_t ph = j & 1;
-        const bool more = j + 1 < nblk;
-        tc::mbar_wait(s_full, ph);   // S_j retired: the K buffer is free
-        if (more) {
-          tc::mbar_expect_tx(k_full, C::NP * C::KV_BYTES);
-#pragma unroll
-          for (int pl = 0; pl < C::NP; ++pl) load_rows(sK + pl * C::KV_BYTES, k_full, colk, (j + 1) * BKV, pl);
-        }
-        tc::mbar_wait(p_full, ph);   // P_j is in shared memory (and S_j has been read out of TMEM)
-        tc::mbar_wait(v_full, ph);
+        const int st = j & 1;
+        tc::mbar_wait(s_full, ph);            // S_j retired: K stage st is free
+        if (j + 2 < nblk) load_k(j + 2);
+        tc::mbar_wait(p_full, ph);            // P_j is in TMEM (and S_j has been read out)
+        tc::mbar_wait(&v_full[st], (j >> 1) & 1);
         tc::tc_fence_after();
-        issue_o();
-        if (more) {
-          tc::mbar_wait(k_full, ph ^ 1);
+        issue_o(st);
+        if (j + 1 < nblk) {
+          tc::mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
           tc::tc_fence_after();
-          issue_s();                 // queued behind P_j V_j on the tensor pipe; overlaps the accumulate of block j
+          issue_s(st ^ 1);                    // queued behind P_j V_j; overlaps the accumulate of block j
         }
-        tc::mbar_wait(o_full, ph);   // P_j V_j retired: V and P buffers are free
-        if (more) {
-          tc::mbar_expect_tx(v_full, C::NP * C::KV_BYTES);
-#pragma unroll
-          for (int pl = 0; pl < C::NP; ++pl) load_rows(sV + pl * C::KV_BYTES, v_full, colv, (j + 1) * BKV, pl);
-        }
+        tc::mbar_wait(o_full, ph);            // P_j V_j retired: V stage st is free
+        if (j + 2 < nblk) load_v(j + 2);
       }
     }
   } else {
-    // ================= softmax / accumulate threads: thread = query row =================
-    const int i = tid;  // row of the tile == TMEM lane
-    int lo = 0, hi = p.seq_len;         // valid key range (tile-relative key index)
+    // ================= softmax / accumulate threads =================
+    // Two threads per query row: thread (row i, half hf) owns keys [32 hf, 32 hf + 32) of every 64-key block and
+    // output dims [32 hf, 32 hf + 32).  The row maximum is agreed through shared memory once per block.
+    const int hf = warp >> 2;
+    const int i = (warp & 3) * 32 + (tid & 31);   // row of the tile == TMEM lane
+    int lo = 0, hi = p.seq_len;                   // valid key range (tile-relative key index)
     bool row_valid;
     int64_t out_row;
     if (p.mode == 0) {
@@ -209,85 +222,83 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       hi = row_valid ? lo + p.seq_len : 0;
       out_row = row_base + i;
     }
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    float o[DH];
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    constexpr int HC = BKV / 2;   // 32 score columns / output dims per thread
+    float o[HC];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) o[d] = 0.f;
+    for (int d = 0; d < HC; ++d) o[d] = 0.f;
     float mrun = -INFINITY, lrun = 0.f;
-    uint8_t* prow_hi = sP + i * 128;
-    const int sw = i & 7;
 
     for (int j = 0; j < nblk; ++j) {
       const uint32_t ph = j & 1;
       tc::mbar_wait(s_full, ph);
       tc::tc_fence_after();
-      float s[BKV];
-      tc::tmem_ld32(tmem_S + lane_off, s);
-      tc::tmem_ld32(tmem_S + lane_off + 32, s + 32);
+      float s[HC];
+      tc::tmem_ld32(tmem_S + lane_off + hf * HC, s);
       tc::tmem_ld_wait();
+      const int k0 = j * BKV + hf * HC;
       float mx = -INFINITY;
+      if (__all_sync(0xffffffffu, k0 >= lo && k0 + HC <= hi)) {
 #pragma unroll
-      for (int c = 0; c < BKV; ++c) {
-        const int kj = j * BKV + c;
-        s[c] = (kj >= lo && kj < hi) ? s[c] * LOG2E : -INFINITY;
-        mx = fmaxf(mx, s[c]);
-      }
-      const float mnew = fmaxf(mrun, mx);
-      const float moff = mnew == -INFINITY ? 0.f : mnew;
-      const float corr = exp2f(mrun - moff);
-      float sum = 0.f;
-#pragma unroll
-      for (int c8 = 0; c8 < BKV / 8; ++c8) {
-        uint32_t ph_[4], pl_[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p0 = exp2f(s[c8 * 8 + 2 * e] - moff);
-          const float p1 = exp2f(s[c8 * 8 + 2 * e + 1] - moff);
-          sum += p0 + p1;
-          __nv_bfloat16 h0, l0, h1, l1;
-          tc::split_bf16(p0, h0, l0);
-          tc::split_bf16(p1, h1, l1);
-          ph_[e] = tc::pack_bf16(h0, h1);
-          pl_[e] = tc::pack_bf16(l0, l1);
+        for (int c = 0; c < HC; ++c) {
+          s[c] *= LOG2E;
+          mx = fmaxf(mx, s[c]);
         }
-        const int off = ((c8 ^ sw) << 4);
-        *reinterpret_cast<uint4*>(prow_hi + off) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
-        if (NSPLIT == 3) *reinterpret_cast<uint4*>(prow_hi + C::P_BYTES + off) = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < HC; ++c) {
+          const int kj = k0 + c;
+          s[c] = (kj >= lo && kj < hi) ? s[c] * LOG2E : -INFINITY;
+          mx = fmaxf(mx, s[c]);
+        }
       }
+      float* xm = xch + (ph * 2) * BQ;
+      xm[hf * BQ + i] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mnew = fmaxf(mrun, fmaxf(mx, xm[(hf ^ 1) * BQ + i]));
+      const float moff = mnew == -INFINITY ? 0.f : mnew;
+      const float corr = tc::ex2_approx(mrun - moff);
+      float sum = 0.f;
+      uint32_t phi[HC / 2], plo[HC / 2];
+#pragma unroll
+      for (int e = 0; e < HC / 2; ++e) {
+        const float p0 = tc::ex2_approx(s[2 * e] - moff);
+        const float p1 = tc::ex2_approx(s[2 * e + 1] - moff);
+        sum += p0 + p1;
+        tc::split_bf16x2(p0, p1, phi[e], plo[e]);
+      }
+      tc::tmem_st16(tmem_P + lane_off + hf * (HC / 2), phi);
+      if (NSPLIT == 3) tc::tmem_st16(tmem_P + lane_off + 32 + hf * (HC / 2), plo);
+      tc::tmem_st_wait();
       lrun = lrun * corr + sum;
       mrun = mnew;
-      tc::fence_proxy_async();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
       tc::tc_fence_before();
       tc::mbar_arrive(p_full);
 
       tc::mbar_wait(o_full, ph);
       tc::tc_fence_after();
+      float ob[HC];
+      tc::tmem_ld32(tmem_O + lane_off + hf * HC, ob);
+      tc::tmem_ld_wait();
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float ob[32];
-        tc::tmem_ld32(tmem_O + lane_off + half * 32, ob);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int d = 0; d < 32; ++d) o[half * 32 + d] = fmaf(o[half * 32 + d], corr, ob[d]);
-      }
+      for (int d = 0; d < HC; ++d) o[d] = fmaf(o[d], corr, ob[d]);
       tc::tc_fence_before();
     }
 
+    // combine the two halves' row sums, gate, split to planes, store this thread's 32 output dims
+    float* xs = xch + ((nblk & 1) * 2) * BQ;
+    xs[hf * BQ + i] = lrun;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float ltot = lrun + xs[(hf ^ 1) * BQ + i];
     if (row_valid) {
       const float gl = p.gates[out_row * p.ldg + h];
-      const float sc = (1.0f / (1.0f + expf(-gl))) / lrun;
-      __nv_bfloat16* op = p.out + out_row * p.ldo + h * DH;
+      const float sc = (1.0f / (1.0f + expf(-gl))) / ltot;
+      __nv_bfloat16* op = p.out + out_row * p.ldo + h * DH + hf * HC;
 #pragma unroll
-      for (int d8 = 0; d8 < DH / 8; ++d8) {
+      for (int d8 = 0; d8 < HC / 8; ++d8) {
         uint32_t hh[4], ll[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          tc::split_bf16(o[d8 * 8 + 2 * e] * sc, h0, l0);
-          tc::split_bf16(o[d8 * 8 + 2 * e + 1] * sc, h1, l1);
-          hh[e] = tc::pack_bf16(h0, h1);
-          ll[e] = tc::pack_bf16(l0, l1);
-        }
+        for (int e = 0; e < 4; ++e) tc::split_bf16x2(o[d8 * 8 + 2 * e] * sc, o[d8 * 8 + 2 * e + 1] * sc, hh[e], ll[e]);
         *reinterpret_cast<uint4*>(op + d8 * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
         if (p.out_planes > 1) *reinterpret_cast<uint4*>(op + p.out_plane + d8 * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
       }
@@ -296,7 +307,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem_base, 128);
+  if (warp == 8) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 template <int NSPLIT>

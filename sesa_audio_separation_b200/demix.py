@@ -43,7 +43,7 @@ class DemixEngine:
     """Device-resident demix of one track.  ``engine_batch`` chunks go through the model per launch
     group; it is a throughput knob only and never changes the result's bookkeeping."""
 
-    def __init__(self, config, model, device, engine_batch=None, world=1, rank=0, progress=None):
+    def __init__(self, config, model, device, engine_batch=None, world=1, rank=0, progress=None, group=None):
         _lib.require_cuda()
         self.model = _unwrap(model)
         self.device = torch.device(device)
@@ -55,7 +55,7 @@ class DemixEngine:
         self.batch_size = int(config.inference.batch_size)
         self.instruments = list(prefer_target_instrument(config))
         self.engine_batch = int(engine_batch or max(1, min(8, self.batch_size * 2)))
-        self.world, self.rank = world, rank
+        self.world, self.rank, self.group = world, rank, group
         self.progress = progress
 
     def run(self, mix, return_counter=False, to_host=True):
@@ -119,7 +119,35 @@ class DemixEngine:
                  _ptr(result), _ptr(counter), st)
         else:
             from .distributed import sharded_overlap_add
-            sharded_overlap_add(self, plan, chunk_out, lo, hi, starts, lens, kinds, result, counter, crop, st)
+            nrows = n_inst * C
+
+            def _range(p0, p1, init, init_p0, mode, out):
+                call('sesa_overlap_add_range', _ptr(chunk_out), _ptr(starts), _ptr(lens), _ptr(kinds), plan.n_chunks,
+                     lo, hi, plan.step, L, plan.fade, _ptr(window), n_inst, C, p0, p1, _ptr(init), init_p0,
+                     init.shape[1] if init is not None else 0, mode, crop, length, _ptr(out), st)
+
+            class _Ops:
+                @staticmethod
+                def raw(p0, p1):
+                    out = torch.empty(nrows, p1 - p0, device=dev, dtype=torch.float32)
+                    _range(p0, p1, None, 0, 1, out)
+                    return out
+
+                @staticmethod
+                def final(p0, p1, init, init_p0):
+                    full = torch.zeros(nrows, length, device=dev, dtype=torch.float32)
+                    _range(p0, p1, init, init_p0, 0, full)
+                    q0 = max(p0, crop) - crop
+                    q1 = max(min(p1, crop + length) - crop, q0)
+                    return full[:, q0:q1]
+            res = sharded_overlap_add(plan, self.world, self.rank, nrows, _Ops, dev, group=self.group)
+            self.plan = plan
+            if res is None:
+                return None
+            result = res.view(n_inst, C, length)
+            if return_counter:
+                call('sesa_overlap_add', _ptr(chunk_out), _ptr(starts), _ptr(lens), _ptr(kinds), plan.n_chunks, plan.step,
+                     L, plan.fade, _ptr(window), n_inst, C, plan.padded, crop, 0, None, _ptr(counter), st)
         self.plan = plan
         if not to_host:
             return (result, counter) if return_counter else result
