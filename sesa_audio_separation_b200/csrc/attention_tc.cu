@@ -25,7 +25,7 @@ constexpr int DH = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 64;
 constexpr int SM_THREADS = 256;   // warps 0-7: softmax / accumulate; thread (row = (warp&3)*32+lane, half = warp>>2)
-constexpr int ATT_THREADS = SM_THREADS + 32;  // warp 8: TMA + MMA issue
+constexpr int ATT_THREADS = SM_THREADS + 64;  // warp 8: MMA issue, warp 9: TMA producer
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnParams {
@@ -52,8 +52,10 @@ struct ACfg {
   static constexpr int OFF_V = OFF_K + KV_STAGES * NP * KV_BYTES;
   static constexpr int OFF_X = OFF_V + KV_STAGES * NP * KV_BYTES;   // float xch[2][2][128]: row max / row sum exchange
   static constexpr int OFF_BAR = OFF_X + 2 * 2 * BQ * 4;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-  // TMEM columns: S fp32 [0,64) | O fp32 [64,128) | P bf16x2: hi [128,160), lo [160,192)
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  // TMEM columns: SP[0] [0,64) | SP[1] [64,128) | O[0] [128,192) | O[1] [192,256).
+  // SP[b] holds the fp32 scores of block j (b = j&1) and is overwritten IN PLACE by P (bf16 pairs: hi in the first
+  // 32 columns, lo in the last 32) once both threads of a row have read their scores.
   static constexpr int TMEM_COLS = 256;
 };
 
@@ -69,12 +71,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
   float* xch = reinterpret_cast<float*>(smem + C::OFF_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* v_full = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;    // [2] TMA -> MMA
+  uint64_t* k_empty = bars + 3;   // [2] MMA (commit) -> TMA
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2] MMA (commit) -> softmax
+  uint64_t* p_full = bars + 11;   // [2] softmax (256 arrivals) -> MMA
+  uint64_t* o_full = bars + 13;   // [2] MMA (commit) -> softmax
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -82,13 +86,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
 
   if (tid == SM_THREADS) {
     tc::mbar_init(q_full, 1);
-    tc::mbar_init(&k_full[0], 1);
-    tc::mbar_init(&k_full[1], 1);
-    tc::mbar_init(&v_full[0], 1);
-    tc::mbar_init(&v_full[1], 1);
-    tc::mbar_init(s_full, 1);
-    tc::mbar_init(p_full, SM_THREADS);
-    tc::mbar_init(o_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&k_full[b], 1);
+      tc::mbar_init(&k_empty[b], 1);
+      tc::mbar_init(&v_full[b], 1);
+      tc::mbar_init(&v_empty[b], 1);
+      tc::mbar_init(&s_full[b], 1);
+      tc::mbar_init(&p_full[b], SM_THREADS);
+      tc::mbar_init(&o_full[b], 1);
+    }
     tc::fence_barrier_init();
   }
   if (warp == 8) {
@@ -99,9 +105,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S = tmem_base;         // fp32 scores, columns [0, 64)
-  const uint32_t tmem_O = tmem_base + 64;    // fp32 block output, columns [64, 128)
-  const uint32_t tmem_P = tmem_base + 128;   // bf16 pairs: hi plane [128,160), lo plane [160,192)
+  const uint32_t tmem_SP = tmem_base;         // + 64*b
+  const uint32_t tmem_O = tmem_base + 128;    // + 64*b
 
   // ---- work item geometry
   int nblk, q0 = 0;
@@ -118,8 +123,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
     nblk = BQ / BKV;
   }
 
-  if (warp == 8) {
-    // ================= control warp: TMA loads + MMA issue =================
+  if (warp == 9) {
+    // ================= TMA producer =================
     if (tc::elect_one()) {
       auto load_rows = [&](uint8_t* dst, uint64_t* bar, int col, int r0, int plane) {
         // 64 rows x 64 columns of one plane (rows beyond the tensor are zero-filled by TMA)
@@ -129,12 +134,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       const int colq = h * DH, colk = p.inner + h * DH, colv = 2 * p.inner + h * DH;
       auto load_k = [&](int j) {
         const int st = j & 1;
+        tc::mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);   // S_{j-2} retired (passes at once for j < 2)
         tc::mbar_expect_tx(&k_full[st], C::NP * C::KV_BYTES);
 #pragma unroll
         for (int pl = 0; pl < C::NP; ++pl) load_rows(sK + (st * C::NP + pl) * C::KV_BYTES, &k_full[st], colk, j * BKV, pl);
       };
       auto load_v = [&](int j) {
         const int st = j & 1;
+        tc::mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);   // P_{j-2} V_{j-2} retired
         tc::mbar_expect_tx(&v_full[st], C::NP * C::KV_BYTES);
 #pragma unroll
         for (int pl = 0; pl < C::NP; ++pl) load_rows(sV + (st * C::NP + pl) * C::KV_BYTES, &v_full[st], colv, j * BKV, pl);
@@ -145,67 +152,68 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
         load_rows(sQ + pl * C::Q_BYTES, q_full, colq, q0, pl);
         load_rows(sQ + pl * C::Q_BYTES + C::KV_BYTES, q_full, colq, q0 + 64, pl);
       }
+      // issue order follows the order in which the tensor pipe frees the stages:
+      // S_0 S_1 PV_0 S_2 PV_1 S_3 ...  =>  K_0 V_0 K_1 V_1 K_2 | K_3 V_2 | K_4 V_3 | ...
       load_k(0);
       load_v(0);
-      if (nblk > 1) {
-        load_k(1);
-        load_v(1);
+      if (nblk > 1) { load_k(1); load_v(1); }
+      if (nblk > 2) load_k(2);
+      for (int j = 2; j < nblk; ++j) {
+        if (j + 1 < nblk) load_k(j + 1);
+        load_v(j);
       }
-
+    }
+  } else if (warp == 8) {
+    // ================= MMA issuer =================
+    if (tc::elect_one()) {
       constexpr uint32_t idesc_s = tc::make_idesc_bf16(BQ, BKV, 0, 0);  // S = Q K^T : both K-major
       constexpr uint32_t idesc_o = tc::make_idesc_bf16(BQ, DH, 0, 1);   // O = P V   : P from TMEM, V MN-major
       const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
-      auto issue_s = [&](int st) {
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        tc::mbar_wait(&k_full[st], (j >> 1) & 1);
+        tc::tc_fence_after();
 #pragma unroll
         for (int prod = 0; prod < NSPLIT; ++prod) {
           const uint32_t qa = aQ + (prod == 2 ? C::Q_BYTES : 0);
           const uint32_t ka = aK + (st * C::NP + (prod == 1 ? 1 : 0)) * C::KV_BYTES;
 #pragma unroll
           for (int ks = 0; ks < DH / 16; ++ks)
-            tc::umma_f16(tmem_S, tc::make_smem_desc_sw128(qa + ks * 32), tc::make_smem_desc_sw128(ka + ks * 32), idesc_s,
-                         (prod | ks) != 0 ? 1u : 0u);
+            tc::umma_f16(tmem_SP + st * 64, tc::make_smem_desc_sw128(qa + ks * 32), tc::make_smem_desc_sw128(ka + ks * 32),
+                         idesc_s, (prod | ks) != 0 ? 1u : 0u);
         }
-        tc::umma_commit(s_full);
+        tc::umma_commit(&s_full[st]);
+        tc::umma_commit(&k_empty[st]);
       };
-      auto issue_o = [&](int st) {
+      tc::mbar_wait(q_full, 0);
+      issue_s(0);
+      if (nblk > 1) issue_s(1);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        tc::mbar_wait(&p_full[st], ph);       // P_j is in TMEM (S_j consumed); O[st] of block j-2 has been read
+        tc::mbar_wait(&v_full[st], ph);
+        tc::tc_fence_after();
 #pragma unroll
         for (int prod = 0; prod < NSPLIT; ++prod) {
-          const uint32_t pa = tmem_P + (prod == 2 ? 32 : 0);
+          const uint32_t pa = tmem_SP + st * 64 + (prod == 2 ? 32 : 0);
           const uint32_t va = aV + (st * C::NP + (prod == 1 ? 1 : 0)) * C::KV_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BKV / 16; ++ks)   // 16 keys = 8 packed TMEM columns of P, 16 rows (2 KB) of V
-            tc::umma_f16_ts(tmem_O, pa + ks * 8, tc::make_smem_desc_sw128(va + ks * 2048, 8192), idesc_o,
+            tc::umma_f16_ts(tmem_O + st * 64, pa + ks * 8, tc::make_smem_desc_sw128(va + ks * 2048, 8192), idesc_o,
                             (prod | ks) != 0 ? 1u : 0u);
         }
-        tc::umma_commit(o_full);
-      };
-
-      tc::mbar_wait(q_full, 0);
-      tc::mbar_wait(&k_full[0], 0);
-      tc::tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nblk; ++j) {
-        const uint32_t ph = j & 1;
-        const int st = j & 1;
-        tc::mbar_wait(s_full, ph);            // S_j retired: K stage st is free
-        if (j + 2 < nblk) load_k(j + 2);
-        tc::mbar_wait(p_full, ph);            // P_j is in TMEM (and S_j has been read out)
-        tc::mbar_wait(&v_full[st], (j >> 1) & 1);
-        tc::tc_fence_after();
-        issue_o(st);
-        if (j + 1 < nblk) {
-          tc::mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
-          tc::tc_fence_after();
-          issue_s(st ^ 1);                    // queued behind P_j V_j; overlaps the accumulate of block j
-        }
-        tc::mbar_wait(o_full, ph);            // P_j V_j retired: V stage st is free
-        if (j + 2 < nblk) load_v(j + 2);
+        tc::umma_commit(&o_full[st]);
+        tc::umma_commit(&v_empty[st]);
+        if (j + 2 < nblk) issue_s(j + 2);     // overwrites SP[st] after P_j V_j (the tensor pipe runs in issue order)
       }
     }
   } else {
     // ================= softmax / accumulate threads =================
     // Two threads per query row: thread (row i, half hf) owns keys [32 hf, 32 hf + 32) of every 64-key block and
     // output dims [32 hf, 32 hf + 32).  The row maximum is agreed through shared memory once per block.
+    // Order per thread: softmax_0, [softmax_j, accumulate_{j-1}] ..., accumulate_{last}: the P V MMA of block j-1
+    // runs under the softmax of block j.
     const int hf = warp >> 2;
     const int i = (warp & 3) * 32 + (tid & 31);   // row of the tile == TMEM lane
     int lo = 0, hi = p.seq_len;                   // valid key range (tile-relative key index)
@@ -227,14 +235,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
     float o[HC];
 #pragma unroll
     for (int d = 0; d < HC; ++d) o[d] = 0.f;
-    float mrun = -INFINITY, lrun = 0.f;
+    float mrun = -INFINITY, lrun = 0.f, corr_prev = 0.f;
+
+    auto accumulate = [&](int jb) {   // o = o * corr(jb) + O_blk(jb)
+      const int st = jb & 1;
+      tc::mbar_wait(&o_full[st], (jb >> 1) & 1);
+      tc::tc_fence_after();
+      float ob[HC];
+      tc::tmem_ld32(tmem_O + st * 64 + lane_off + hf * HC, ob);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < HC; ++d) o[d] = fmaf(o[d], corr_prev, ob[d]);
+      tc::tc_fence_before();
+    };
 
     for (int j = 0; j < nblk; ++j) {
-      const uint32_t ph = j & 1;
-      tc::mbar_wait(s_full, ph);
+      const int st = j & 1;
+      tc::mbar_wait(&s_full[st], (j >> 1) & 1);
       tc::tc_fence_after();
       float s[HC];
-      tc::tmem_ld32(tmem_S + lane_off + hf * HC, s);
+      tc::tmem_ld32(tmem_SP + st * 64 + lane_off + hf * HC, s);
       tc::tmem_ld_wait();
       const int k0 = j * BKV + hf * HC;
       float mx = -INFINITY;
@@ -252,9 +272,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
           mx = fmaxf(mx, s[c]);
         }
       }
-      float* xm = xch + (ph * 2) * BQ;
+      float* xm = xch + (st * 2) * BQ;
       xm[hf * BQ + i] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc::tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // also: both halves of every row have read their scores
+      tc::tc_fence_after();
       const float mnew = fmaxf(mrun, fmaxf(mx, xm[(hf ^ 1) * BQ + i]));
       const float moff = mnew == -INFINITY ? 0.f : mnew;
       const float corr = tc::ex2_approx(mrun - moff);
@@ -267,23 +289,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
         sum += p0 + p1;
         tc::split_bf16x2(p0, p1, phi[e], plo[e]);
       }
-      tc::tmem_st16(tmem_P + lane_off + hf * (HC / 2), phi);
-      if (NSPLIT == 3) tc::tmem_st16(tmem_P + lane_off + 32 + hf * (HC / 2), plo);
+      tc::tmem_st16(tmem_SP + st * 64 + lane_off + hf * (HC / 2), phi);
+      if (NSPLIT == 3) tc::tmem_st16(tmem_SP + st * 64 + lane_off + 32 + hf * (HC / 2), plo);
       tc::tmem_st_wait();
       lrun = lrun * corr + sum;
       mrun = mnew;
       tc::tc_fence_before();
-      tc::mbar_arrive(p_full);
-
-      tc::mbar_wait(o_full, ph);
-      tc::tc_fence_after();
-      float ob[HC];
-      tc::tmem_ld32(tmem_O + lane_off + hf * HC, ob);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int d = 0; d < HC; ++d) o[d] = fmaf(o[d], corr, ob[d]);
-      tc::tc_fence_before();
+      tc::mbar_arrive(&p_full[st]);
+      if (j > 0) accumulate(j - 1);
+      corr_prev = corr;
     }
+    accumulate(nblk - 1);
 
     // combine the two halves' row sums, gate, split to planes, store this thread's 32 output dims
     float* xs = xch + ((nblk & 1) * 2) * BQ;
