@@ -113,6 +113,16 @@ typedef struct sesa_tc_problem {
   void* P;               /* bf16 plane output [out_planes][M][ldp] or NULL (feeds the next tensor-core op) */
   int64_t lda, a_plane, ldw, w_plane, ldc, ldp, p_plane; /* element strides; *_plane = plane-to-plane distance */
   int32_t M, N, K, _pad;
+  /* Implicit-GEMM convolution over a channels-last activation (conv_taps == 0: plain GEMM, fields ignored).
+   * A = bf16 planes [planes][B][inT][inF][lda] (lda >= conv_cin channels); output row m = (b*T + t)*F + f;
+   * tap i reads input pixel (t*stride + conv_dt[i], f*stride + conv_df[i]), zero outside the grid (the padding of
+   * nn.Conv2d, mdx23c_tfc_tdf_v3.py:111,123); W columns are [tap][round_up(conv_cin, 64)] (zero padded), so
+   * K = conv_taps * round_up(conv_cin, 64).  F must divide 128 or be a multiple of 128 (tile = 128 pixels). */
+  int32_t conv_taps, conv_cin, conv_B, conv_T, conv_F, conv_inT, conv_inF, conv_stride;
+  int32_t conv_dt[9], conv_df[9];
+  /* Output row remap: 0 = row m; 1 = 2x up-sampling scatter of nn.ConvTranspose2d(kernel = stride = 2)
+   * (mdx23c_tfc_tdf_v3.py:80): row = (2*(m / rm_F) + rm_dt) * 2*rm_F + 2*(m % rm_F) + rm_df. */
+  int32_t row_map, rm_F, rm_dt, rm_df;
 } sesa_tc_problem;
 
 /* Bytes of the device-side group table for n_groups problems. */
@@ -145,6 +155,32 @@ int sesa_prep_rows(const float* x, int64_t ldx, int64_t rows, int dim, int norma
                    float* gates, int64_t ldg, float* rowinv, void* stream);
 /* bf16 hi/lo planes of a weight matrix w[rows][cols] -> planes[2][rows][ldp] (zero padded to ldp). */
 int sesa_split_weight(const float* w, int64_t rows, int64_t cols, void* planes, int64_t ldp, void* stream);
+
+/* ---- MDX23C (TFC_TDF_net) support: channels-last activations x[b][t][f][c] ----------------------------------- */
+/* InstanceNorm2d statistics (get_norm 'InstanceNorm', mdx23c_tfc_tdf_v3.py:47-59: biased variance, eps 1e-5) per
+ * (b, c): stats[b][c] = (mean, 1/sqrt(var+eps)).  layout 0: x[(b*n1+i)*ld + c] (n2 = 1); layout 1:
+ * x[((b*n1+i)*C + c)*n2 + j].  scratch: 2*batch*channels doubles. */
+int sesa_instnorm_stats(const float* x, int layout, int batch, int64_t n1, int channels, int n2, int64_t ld,
+                        double* scratch, float* stats, float eps, void* stream);
+/* y = act((x - mean) * rstd * gamma + beta) split into bf16 hi/lo planes (the "norm -> act" prologue of every conv /
+ * Linear of TFC_TDF, :104-128).  stats == NULL skips the normalisation; act: SESA_ACT_NONE, SESA_ACT_GELU or 4 (ReLU).
+ * mode 0: channels-last in and out (n2 = 1): planes[(b*n1+i)*ldp + c];
+ * mode 1: channels-last in (n1 = T, n2 = F, x[((b*T+t)*F + f)*ld + c]) -> channel-major planes[((b*T+t)*C + c)*ldp + f];
+ * mode 2: channel-major in and out: x[((b*n1+i)*C + c)*n2 + j] -> planes[((b*n1+i)*C + c)*ldp + j]. */
+int sesa_norm_act_split(const float* x, int mode, int batch, int64_t n1, int channels, int n2, int64_t ld,
+                        const float* stats, const float* gamma, const float* beta, int act, void* planes, int64_t ldp,
+                        int64_t p_plane, void* stream);
+/* x[(bt*F + f)*ld + c] += g[(bt*C + c)*F + f]: "x = x + tdf(x)" (:134) with the TDF output channel-major. */
+int sesa_transpose_add(float* x, const float* g, int64_t bt, int F, int channels, int64_t ld, void* stream);
+/* cac2cws (:191-196): spec (sesa_stft layout 0, [bt][f_full][c2]) -> mix[bt][fs][c2*k + kk], f_full = kk*fs + f'. */
+int sesa_mdx_pack(const float* spec, int64_t bt, int f_full, int fs, int k, int c2, float* mix, void* stream);
+/* planes[r] = split([mix[r] | x[r] * first[r]]): "x * first_conv_out" and cat([mix, x]) (:228-230). */
+int sesa_mdx_final_concat(const float* mix, int ch, const float* x, int64_t ldx, const float* first, int64_t ldf,
+                          int channels, int64_t rows, void* planes, int64_t ldp, int64_t p_plane, void* stream);
+/* cws2cac (:198-203) + zero padding of STFT.inverse (:36-38): y[bt][fs][nt*c2*k] -> out[(b*nt+n)][t][f_full][c2]
+ * (the layout sesa_mask_istft mode 2 reads). */
+int sesa_mdx_unpack(const float* y, int64_t batch, int64_t frames, int fs, int k, int c2, int nt, int f_full,
+                    float* out, void* stream);
 
 /* ---- windowed overlap-add of chunk outputs (utils.py:432-464) ------------------------------- */
 /* chunk_out[k][n][c][L]; result[n][c][out_len] = sum_k (ascending) y*w / sum_k w over padded positions

@@ -31,12 +31,16 @@ GEMM_GROUP_DTYPE = np.dtype([('A', '<u8'), ('W', '<u8'), ('bias', '<u8'), ('C', 
                              ('lda', '<i8'), ('ldw', '<i8'), ('ldc', '<i8')])
 assert GEMM_GROUP_DTYPE.itemsize == 72
 
-# numpy mirror of struct sesa_tc_problem (120 bytes)
+# numpy mirror of struct sesa_tc_problem (240 bytes)
 TC_PROBLEM_DTYPE = np.dtype([('A', '<u8'), ('W', '<u8'), ('bias', '<u8'), ('rowscale', '<u8'), ('C', '<u8'),
                              ('P', '<u8'), ('lda', '<i8'), ('a_plane', '<i8'), ('ldw', '<i8'), ('w_plane', '<i8'),
                              ('ldc', '<i8'), ('ldp', '<i8'), ('p_plane', '<i8'),
-                             ('M', '<i4'), ('N', '<i4'), ('K', '<i4'), ('_pad', '<i4')])
-assert TC_PROBLEM_DTYPE.itemsize == 120
+                             ('M', '<i4'), ('N', '<i4'), ('K', '<i4'), ('_pad', '<i4'),
+                             ('conv_taps', '<i4'), ('conv_cin', '<i4'), ('conv_B', '<i4'), ('conv_T', '<i4'),
+                             ('conv_F', '<i4'), ('conv_inT', '<i4'), ('conv_inF', '<i4'), ('conv_stride', '<i4'),
+                             ('conv_dt', '<i4', (9,)), ('conv_df', '<i4', (9,)),
+                             ('row_map', '<i4'), ('rm_F', '<i4'), ('rm_dt', '<i4'), ('rm_df', '<i4')])
+assert TC_PROBLEM_DTYPE.itemsize == 240
 
 _SIGS = {
     'sesa_abi_version': (c_int, []),
@@ -66,6 +70,15 @@ _SIGS = {
     'sesa_overlap_add': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int,
                                  c_void_p, c_int, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                  c_void_p]),
+    'sesa_instnorm_stats': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                    ctypes.c_float, c_void_p]),
+    'sesa_norm_act_split': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_void_p, c_int64, c_int64, c_void_p]),
+    'sesa_transpose_add': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),
+    'sesa_mdx_pack': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'sesa_mdx_final_concat': (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_void_p,
+                                      c_int64, c_int64, c_void_p]),
+    'sesa_mdx_unpack': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'sesa_overlap_add_range': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64,
                                        c_int, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                        c_int, c_int64, c_int64, c_void_p, c_void_p]),
@@ -103,7 +116,7 @@ def check(status):
 # ---- launch accounting / per-kernel-class timing (bench.py, profiling); off by default
 LAUNCHES = 0
 _profile = None   # dict: class -> [ (start_event, end_event), ... ] when enabled
-_CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_attention_simt': 'attention',
+_CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_instnorm_stats': 'norm', 'sesa_norm_act_split': 'norm', 'sesa_transpose_add': 'norm', 'sesa_attention_simt': 'attention',
           'sesa_attention_tc': 'attention', 'sesa_stft': 'stft', 'sesa_mask_istft': 'mask_istft',
           'sesa_overlap_add': 'overlap_add', 'sesa_overlap_add_range': 'overlap_add', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}
 

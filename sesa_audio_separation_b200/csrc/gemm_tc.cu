@@ -38,6 +38,10 @@ struct alignas(128) TcGroup {
   int64_t ldc, ldp, p_plane;
   int32_t M, N, K, tile_begin;
   int32_t n_blocks, k_blocks, tile_end, _r;
+  // implicit-GEMM convolution (taps == 0: plain GEMM; mapA is then 3-D, else 5-D (c, f, t, b, plane))
+  int32_t taps, kb_per_tap, conv_T, conv_F, conv_stride;
+  int32_t row_map, rm_F, rm_dt, rm_df;
+  int32_t tap_dt[9], tap_df[9];
 };
 static_assert(sizeof(TcGroup) % 128 == 0, "table entries must keep the tensor maps 128-byte aligned");
 
@@ -154,13 +158,33 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
         const int t = tile - g->tile_begin;
         const int mb = t / g->n_blocks, nb = t % g->n_blocks;
         const int kbs = g->k_blocks;
+        const int taps = g->taps;
+        int cf0 = 0, ct0 = 0, cb = 0, kbpt = 1;
+        if (taps > 0) {   // output pixel (b, t0, f0) of the tile's first row
+          const int m0 = mb * BM;
+          const int q = m0 / g->conv_F;
+          cf0 = (m0 - q * g->conv_F) * g->conv_stride;
+          cb = q / g->conv_T;
+          ct0 = (q - cb * g->conv_T) * g->conv_stride;
+          kbpt = g->kb_per_tap;
+        }
         for (int kb = 0; kb < kbs; ++kb) {
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           tc::mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           uint8_t* sa = stage_base + s * C::STAGE_BYTES;
           uint8_t* sb = sa + C::NP * C::A_BYTES;
+          if (taps > 0) {
+            // implicit im2col: the tap is a shifted TMA box over the channels-last activation; coordinates outside
+            // the grid are zero-filled by TMA, which is exactly the convolution's zero padding
+            const int tap = kb / kbpt;
+            const int c0 = (kb - tap * kbpt) * BK;
 #pragma unroll
-          for (int p = 0; p < C::NP; ++p) tc::tma_load_3d(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], kb * BK, mb * BM, p);
+            for (int p = 0; p < C::NP; ++p)
+              tc::tma_load_5d(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], c0, cf0 + g->tap_df[tap], ct0 + g->tap_dt[tap], cb, p);
+          } else {
+#pragma unroll
+            for (int p = 0; p < C::NP; ++p) tc::tma_load_3d(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], kb * BK, mb * BM, p);
+          }
 #pragma unroll
           for (int p = 0; p < C::NP; ++p) tc::tma_load_3d(sb + p * C::B_BYTES, &g->mapW, &full_bar[s], kb * BK, nb * BN, p);
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
@@ -233,6 +257,12 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       const float rs = (g->rowscale != nullptr && row_ok) ? g->rowscale[m] : 1.0f;
       int pos = 0;
       if ((FLAVOR == F_ROT || FLAVOR == F_GENERIC) && ep.rot_cols > 0) pos = (m / ep.pos_div) % ep.pos_mod;
+      const int row_map = g->row_map, rm_F = g->rm_F, rm_dt = g->rm_dt, rm_df = g->rm_df;
+      auto out_row = [&](int mm) -> int64_t {
+        if (row_map == 0) return mm;
+        const int q = mm / rm_F;
+        return (int64_t)(2 * q + rm_dt) * (2 * rm_F) + 2 * (mm - q * rm_F) + rm_df;
+      };
       const bool c_vec = Cp == nullptr || ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
       const bool p_vec = Pp == nullptr || ((ldp & 3) == 0 && (p_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(Pp) & 7) == 0);
       constexpr bool kGeneric = FLAVOR == F_GENERIC;
@@ -270,7 +300,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
           for (int it = 0; it < 4; ++it) {
             const int mm = m_base + it * 8 + (lane >> 2);
             res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (mm < M && colb + 3 < N) res[it] = *reinterpret_cast<const float4*>(Cp + (int64_t)mm * ldc + colb);
+            if (mm < M && colb + 3 < N) res[it] = *reinterpret_cast<const float4*>(Cp + out_row(mm) * ldc + colb);
           }
         }
         float4 rt4[4];
@@ -323,14 +353,15 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             const int mm = m_base + r;
             float4 o = lds128(stage + r * (EPI_COLS * 4) + ((c4 ^ ((r >> 1) & 3)) << 4));
             if (mm >= M || colb >= N) continue;
+            const int64_t orow = out_row(mm);
             if (colb + 3 < N) {
               if (ep.residual) { o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w; }
-              if (Cp != nullptr) *reinterpret_cast<float4*>(Cp + (int64_t)mm * ldc + colb) = o;
+              if (Cp != nullptr) *reinterpret_cast<float4*>(Cp + orow * ldc + colb) = o;
               if (Pp != nullptr) {
                 __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
                 tc::split_bf16(o.x, h0, l0); tc::split_bf16(o.y, h1, l1);
                 tc::split_bf16(o.z, h2, l2); tc::split_bf16(o.w, h3, l3);
-                __nv_bfloat16* pr = Pp + (int64_t)mm * ldp + colb;
+                __nv_bfloat16* pr = Pp + orow * ldp + colb;
                 *reinterpret_cast<uint2*>(pr) = make_uint2(tc::pack_bf16(h0, h1), tc::pack_bf16(h2, h3));
                 if (out_planes > 1) *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(tc::pack_bf16(l0, l1), tc::pack_bf16(l2, l3));
               }
@@ -339,15 +370,15 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               for (int e = 0; e < 4 && colb + e < N; ++e) {
                 float val = ov[e];
                 if (Cp != nullptr) {
-                  float* cp = Cp + (int64_t)mm * ldc + colb + e;
+                  float* cp = Cp + orow * ldc + colb + e;
                   if (ep.residual) val += *cp;
                   *cp = val;
                 }
                 if (Pp != nullptr) {
                   __nv_bfloat16 h, l;
                   tc::split_bf16(val, h, l);
-                  Pp[(int64_t)mm * ldp + colb + e] = h;
-                  if (out_planes > 1) Pp[(int64_t)mm * ldp + p_plane + colb + e] = l;
+                  Pp[orow * ldp + colb + e] = h;
+                  if (out_planes > 1) Pp[orow * ldp + p_plane + colb + e] = l;
                 }
               }
             }
@@ -368,15 +399,15 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             if (j < width && nbase + j < nlimit) {
               float val = v[j];
               if (Cp != nullptr) {
-                float* cp = Cp + (int64_t)m * ldc + nbase + j;
+                float* cp = Cp + out_row(m) * ldc + nbase + j;
                 if (ep.residual) val += *cp;
                 *cp = val;
               }
               if (Pp != nullptr) {
                 __nv_bfloat16 h, l;
                 tc::split_bf16(val, h, l);
-                Pp[(int64_t)m * ldp + nbase + j] = h;
-                if (out_planes > 1) Pp[(int64_t)m * ldp + p_plane + nbase + j] = l;
+                Pp[out_row(m) * ldp + nbase + j] = h;
+                if (out_planes > 1) Pp[out_row(m) * ldp + p_plane + nbase + j] = l;
               }
             }
           }
@@ -453,7 +484,7 @@ sesa_encode_tiled_fn sesa_get_encode_tiled() {
 }
 
 int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                        const uint64_t* strides_bytes, const uint32_t* box) {
+                        const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   sesa_encode_tiled_fn enc = sesa_get_encode_tiled();
   if (enc == nullptr) {
     sesa_set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -465,7 +496,7 @@ int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides != nullptr ? elem_strides[i] : 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
@@ -496,16 +527,52 @@ extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int b
                    "sesa_gemm_tc_build: problem %d: operand strides must be multiples of 8 bf16 elements", i);
     SESA_CHECK_ARG((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.W) & 15) == 0,
                    "sesa_gemm_tc_build: problem %d: operands must be 16-byte aligned", i);
-    SESA_CHECK_ARG(p.lda >= p.K && p.ldw >= p.K, "sesa_gemm_tc_build: problem %d: row stride smaller than K", i);
+    SESA_CHECK_ARG(p.ldw >= p.K, "sesa_gemm_tc_build: problem %d: weight row stride smaller than K", i);
     TcGroup g;
     memset(&g, 0, sizeof(g));
-    // The K extent is rounded up to the row stride where possible so that partial 64-wide slabs read the
-    // zero padding of the planes instead of relying on out-of-bounds fill alone (both give zeros).
-    const uint64_t dimsA[3] = {(uint64_t)p.K, (uint64_t)p.M, 2};
-    const uint64_t strA[2] = {(uint64_t)p.lda * 2, (uint64_t)(p.a_plane > 0 ? p.a_plane : p.lda * (int64_t)p.M) * 2};
-    const uint32_t boxA[3] = {BK, BM, 1};
-    int rc = sesa_make_tmap_bf16(&g.mapA, p.A, 3, dimsA, strA, boxA);
-    if (rc != SESA_OK) return rc;
+    int rc;
+    if (p.conv_taps > 0) {
+      const int F = p.conv_F, T = p.conv_T, s = p.conv_stride;
+      SESA_CHECK_ARG(p.conv_taps <= 9 && p.conv_cin > 0 && p.conv_B > 0 && T > 0 && F > 0 && (s == 1 || s == 2),
+                     "sesa_gemm_tc_build: problem %d: bad convolution geometry", i);
+      SESA_CHECK_ARG((int64_t)p.conv_B * T * F == p.M, "sesa_gemm_tc_build: problem %d: M != B*T*F", i);
+      const int box_f = F < BM ? F : BM;
+      const int box_t = BM / box_f;
+      SESA_CHECK_ARG((F >= BM ? F % BM == 0 : BM % F == 0) && T % box_t == 0,
+                     "sesa_gemm_tc_build: problem %d: a 128-pixel tile must cover whole rows of the %d x %d grid", i, T, F);
+      const int kbpt = (p.conv_cin + BK - 1) / BK;
+      SESA_CHECK_ARG(p.K == p.conv_taps * kbpt * BK, "sesa_gemm_tc_build: problem %d: K must be taps*round_up(cin,64)", i);
+      SESA_CHECK_ARG(p.lda >= p.conv_cin, "sesa_gemm_tc_build: problem %d: channel stride smaller than cin", i);
+      const uint64_t dimsA[5] = {(uint64_t)p.conv_cin, (uint64_t)p.conv_inF, (uint64_t)p.conv_inT, (uint64_t)p.conv_B, 2};
+      const uint64_t strA[4] = {(uint64_t)p.lda * 2, (uint64_t)p.lda * 2 * p.conv_inF,
+                                (uint64_t)p.lda * 2 * p.conv_inF * p.conv_inT,
+                                (uint64_t)(p.a_plane > 0 ? p.a_plane : p.lda * (int64_t)p.conv_inF * p.conv_inT * p.conv_B) * 2};
+      const uint32_t boxA[5] = {BK, (uint32_t)(box_f * s), (uint32_t)(box_t * s), 1, 1};
+      const uint32_t esA[5] = {1, (uint32_t)s, (uint32_t)s, 1, 1};
+      rc = sesa_make_tmap_bf16(&g.mapA, p.A, 5, dimsA, strA, boxA, esA);
+      if (rc != SESA_OK) return rc;
+      g.taps = p.conv_taps;
+      g.kb_per_tap = kbpt;
+      g.conv_T = T;
+      g.conv_F = F;
+      g.conv_stride = s;
+      for (int k = 0; k < 9; ++k) {
+        g.tap_dt[k] = p.conv_dt[k];
+        g.tap_df[k] = p.conv_df[k];
+      }
+    } else {
+      SESA_CHECK_ARG(p.lda >= p.K, "sesa_gemm_tc_build: problem %d: row stride smaller than K", i);
+      const uint64_t dimsA[3] = {(uint64_t)p.K, (uint64_t)p.M, 2};
+      const uint64_t strA[2] = {(uint64_t)p.lda * 2, (uint64_t)(p.a_plane > 0 ? p.a_plane : p.lda * (int64_t)p.M) * 2};
+      const uint32_t boxA[3] = {BK, BM, 1};
+      rc = sesa_make_tmap_bf16(&g.mapA, p.A, 3, dimsA, strA, boxA);
+      if (rc != SESA_OK) return rc;
+    }
+    SESA_CHECK_ARG(p.row_map == 0 || (p.row_map == 1 && p.rm_F > 0), "sesa_gemm_tc_build: problem %d: bad row_map", i);
+    g.row_map = p.row_map;
+    g.rm_F = p.rm_F;
+    g.rm_dt = p.rm_dt;
+    g.rm_df = p.rm_df;
     const uint64_t dimsW[3] = {(uint64_t)p.K, (uint64_t)p.N, 2};
     const uint64_t strW[2] = {(uint64_t)p.ldw * 2, (uint64_t)(p.w_plane > 0 ? p.w_plane : p.ldw * (int64_t)p.N) * 2};
     const uint32_t boxW[3] = {BK, (uint32_t)block_n, 1};

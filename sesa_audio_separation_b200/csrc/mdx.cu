@@ -1,0 +1,344 @@
+// MDX23C (TFC_TDF_net, models/mdx23c_tfc_tdf_v3.py:100-242) support kernels.
+//
+// The convolutions and Linears of the U-Net run as tensor-core GEMMs (gemm_tc.cu: implicit-GEMM taps through TMA,
+// plain GEMMs for 1x1 convs and the TDF Linears).  Activations live channels-last, x[b][t][f][c] fp32, so every
+// "norm -> act -> conv" prologue of the reference (get_norm/get_act, :47-71) is ONE elementwise pass that applies
+// InstanceNorm2d statistics + affine + GELU and writes the bf16 hi/lo planes the GEMM's TMA loads consume; the
+// zero padding of the 3x3 convolutions then falls out of TMA's out-of-bounds fill on the already-activated planes.
+#include "common.cuh"
+#include "sesa_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float gelu_exact(float x) {
+  // same 14-instruction exact-erf GELU as the GEMM epilogue (gemm_tc.cu: gelu_fast)
+  const float u = fminf(fabsf(x), 6.0f);
+  float r = -2.834913403e-06f;
+  r = fmaf(r, u, 3.937759539e-05f);
+  r = fmaf(r, u, -1.861794008e-04f);
+  r = fmaf(r, u, -1.369391393e-04f);
+  r = fmaf(r, u, 7.063424215e-03f);
+  r = fmaf(r, u, -5.249617994e-02f);
+  r = fmaf(r, u, -4.592081904e-01f);
+  r = fmaf(r, u, -1.151105165e+00f);
+  const float e = exp2f(u * r);
+  return x * fmaf(0.5f, copysignf(1.0f - e, x), 0.5f);
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == SESA_ACT_GELU) return gelu_exact(v);
+  if (act == 4) return fmaxf(v, 0.f);  // relu
+  return v;
+}
+
+// ---- InstanceNorm2d statistics: per (b, c) over all positions ---------------------------------------------
+// layout 0 (channels-last): element (b, i, c) at x[(b*n1 + i)*ld + c]
+// layout 1 (channel-major rows): element (b, i, c, j) at x[((b*n1 + i)*C + c)*n2 + j]
+__global__ void __launch_bounds__(256) instnorm_acc_kernel(const float* __restrict__ x, int layout, int B, int64_t n1, int C,
+                                                           int n2, int64_t ld, int64_t chunk, double* __restrict__ acc) {
+  const int b = blockIdx.y;
+  const int64_t i0 = (int64_t)blockIdx.x * chunk;
+  const int64_t i1 = min(n1, i0 + chunk);
+  if (layout == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f, ss = 0.f;
+      const float* p = x + ((int64_t)b * n1 + i0) * ld + c;
+      for (int64_t i = i0; i < i1; ++i, p += ld) {
+        const float v = *p;
+        s += v;
+        ss = fmaf(v, v, ss);
+      }
+      atomicAdd(&acc[((int64_t)b * C + c) * 2], (double)s);
+      atomicAdd(&acc[((int64_t)b * C + c) * 2 + 1], (double)ss);
+    }
+  } else {
+    // one warp per (i, c) row of n2 contiguous values
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int c = warp; c < C; c += nw) {
+      float s = 0.f, ss = 0.f;
+      for (int64_t i = i0; i < i1; ++i) {
+        const float* p = x + (((int64_t)b * n1 + i) * C + c) * n2;
+        for (int j = lane; j < n2; j += 32) {
+          const float v = p[j];
+          s += v;
+          ss = fmaf(v, v, ss);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      }
+      if (lane == 0) {
+        atomicAdd(&acc[((int64_t)b * C + c) * 2], (double)s);
+        atomicAdd(&acc[((int64_t)b * C + c) * 2 + 1], (double)ss);
+      }
+    }
+  }
+}
+
+__global__ void instnorm_finalize_kernel(const double* __restrict__ acc, int n, double inv_count, float eps,
+                                         float2* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mean = acc[2 * i] * inv_count;
+  double var = acc[2 * i + 1] * inv_count - mean * mean;  // biased variance, as nn.InstanceNorm2d
+  if (var < 0) var = 0;
+  stats[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+// ---- norm + affine + activation + bf16 split -------------------------------------------------------------
+// mode 0: x[(b*n1+i)*ld + c]          -> planes[(b*n1+i)*ldp + c]             (channels-last, same layout)
+// mode 2: x[((b*n1+i)*C + c)*n2 + j]  -> planes[((b*n1+i)*C + c)*ldp + j]     (channel-major rows, same layout)
+__global__ void __launch_bounds__(256) norm_act_split_kernel(const float* __restrict__ x, int mode, int64_t rows, int C,
+                                                             int n2, int64_t n1, int64_t ld, const float2* __restrict__ stats,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             int act, __nv_bfloat16* __restrict__ planes, int64_t ldp,
+                                                             int64_t p_plane) {
+  // 4 consecutive inner elements per thread
+  const int inner = mode == 0 ? C : n2;
+  const int64_t quads = (int64_t)(inner >> 2);
+  const int64_t total = rows * quads;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / quads;
+    const int q = (int)(idx - r * quads) * 4;
+    float4 v;
+    float o[4];
+    if (mode == 0) {
+      const int64_t b = r / n1;
+      v = *reinterpret_cast<const float4*>(x + r * ld + q);
+      const float in[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float y = in[e];
+        if (stats != nullptr) {
+          const float2 st = stats[b * C + q + e];
+          y = (y - st.x) * st.y * gamma[q + e] + beta[q + e];
+        }
+        o[e] = apply_act(y, act);
+      }
+    } else {
+      const int64_t bc = r;                 // row index = (b*n1 + i)*C + c
+      const int c = (int)(bc % C);
+      const int64_t b = bc / ((int64_t)C * n1);
+      v = *reinterpret_cast<const float4*>(x + r * n2 + q);
+      const float in[4] = {v.x, v.y, v.z, v.w};
+      float2 st = make_float2(0.f, 1.f);
+      float g = 1.f, be = 0.f;
+      if (stats != nullptr) {
+        st = stats[b * C + c];
+        g = gamma[c];
+        be = beta[c];
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = apply_act((in[e] - st.x) * st.y * g + be, act);
+    }
+    uint32_t h0, l0, h1, l1;
+    tc::split_bf16x2(o[0], o[1], h0, l0);
+    tc::split_bf16x2(o[2], o[3], h1, l1);
+    __nv_bfloat16* pr = planes + r * ldp + q;
+    *reinterpret_cast<uint2*>(pr) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(l0, l1);
+  }
+}
+
+// mode 1: channels-last x[(bt*F + f)*ld + c] -> channel-major planes[(bt*C + c)*ldp + f]   (TDF input, :117-119)
+__global__ void __launch_bounds__(256) norm_act_split_tr_kernel(const float* __restrict__ x, int64_t BT, int F, int C,
+                                                                int64_t T, int64_t ld, const float2* __restrict__ stats,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int act,
+                                                                __nv_bfloat16* __restrict__ planes, int64_t ldp,
+                                                                int64_t p_plane) {
+  __shared__ float tile[32][33];
+  const int64_t bt = blockIdx.z;
+  const int f0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
+  const int64_t b = bt / T;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int f = f0 + ty + 8 * k, c = c0 + tx;
+    float y = 0.f;
+    if (f < F && c < C) {
+      y = x[(bt * F + f) * ld + c];
+      if (stats != nullptr) {
+        const float2 st = stats[b * C + c];
+        y = (y - st.x) * st.y * gamma[c] + beta[c];
+      }
+      y = apply_act(y, act);
+    }
+    tile[ty + 8 * k][tx] = y;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, f = f0 + tx;
+    if (c < C && f < F) {
+      __nv_bfloat16 h, l;
+      tc::split_bf16(tile[tx][ty + 8 * k], h, l);
+      const int64_t o = (bt * C + c) * ldp + f;
+      planes[o] = h;
+      planes[o + p_plane] = l;
+    }
+  }
+}
+
+// x[(bt*F + f)*ld + c] += g[(bt*C + c)*F + f]      ("x = x + tdf(x)", :134, with the TDF result channel-major)
+__global__ void __launch_bounds__(256) transpose_add_kernel(float* __restrict__ x, const float* __restrict__ g, int F,
+                                                            int C, int64_t ld) {
+  __shared__ float tile[32][33];
+  const int64_t bt = blockIdx.z;
+  const int f0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, f = f0 + tx;
+    tile[ty + 8 * k][tx] = (c < C && f < F) ? g[(bt * C + c) * F + f] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int f = f0 + ty + 8 * k, c = c0 + tx;
+    if (f < F && c < C) x[(bt * F + f) * ld + c] += tile[tx][ty + 8 * k];
+  }
+}
+
+// spec (sesa_stft layout 0) [bt][f_full][c2] -> mix[bt][f'][c2*k + kk], f_full = kk*Fs + f'   (cac2cws, :191-196)
+__global__ void mdx_pack_kernel(const float* __restrict__ spec, int64_t BT, int F_full, int Fs, int k, int c2,
+                                float* __restrict__ mix) {
+  const int ch = c2 * k;
+  const int64_t total = BT * Fs * ch;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % ch);
+    const int64_t r = i / ch;
+    const int fs = (int)(r % Fs);
+    const int64_t bt = r / Fs;
+    const int co = cc / k, kk = cc - co * k;
+    mix[i] = spec[(bt * F_full + (int64_t)kk * Fs + fs) * c2 + co];
+  }
+}
+
+// planes[r][0:ch] = split(mix[r]), planes[r][ch:ch+C] = split(x[r] * first[r])   ("x * first_conv_out", cat(mix, x): :228-230)
+__global__ void mdx_final_concat_kernel(const float* __restrict__ mix, int ch, const float* __restrict__ x, int64_t ldx,
+                                        const float* __restrict__ first, int64_t ldf, int C, int64_t rows,
+                                        __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t p_plane) {
+  const int w = ch + C;
+  const int64_t total = rows * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % w);
+    const int64_t r = i / w;
+    const float v = j < ch ? mix[r * ch + j] : x[r * ldx + (j - ch)] * first[r * ldf + (j - ch)];
+    __nv_bfloat16 h, l;
+    tc::split_bf16(v, h, l);
+    planes[r * ldp + j] = h;
+    planes[r * ldp + j + p_plane] = l;
+  }
+}
+
+// y[bt][f'][n*ch + c2o*k + kk] -> out[(b*nt + n)][t][f_full][c2o], zero for f_full >= k*Fs   (cws2cac :198-203 + the
+// zero padding of STFT.inverse :36-38), i.e. the layout sesa_mask_istft mode 2 reads.
+__global__ void mdx_unpack_kernel(const float* __restrict__ y, int64_t B, int64_t T, int Fs, int k, int c2, int nt,
+                                  int F_full, float* __restrict__ out) {
+  const int64_t total = B * nt * T * F_full * c2;
+  const int ch = c2 * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % c2);
+    int64_t r = i / c2;
+    const int ff = (int)(r % F_full);
+    r /= F_full;
+    const int64_t t = r % T;
+    r /= T;
+    const int n = (int)(r % nt);
+    const int64_t b = r / nt;
+    float v = 0.f;
+    if (ff < k * Fs) {
+      const int kk = ff / Fs, fs = ff - kk * Fs;
+      v = y[((b * T + t) * Fs + fs) * (int64_t)(nt * ch) + n * ch + co * k + kk];
+    }
+    out[i] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int sesa_instnorm_stats(const float* x, int layout, int batch, int64_t n1, int channels, int n2, int64_t ld,
+                                   double* scratch, float* stats, float eps, void* stream) {
+  SESA_CHECK_ARG(layout == 0 || layout == 1, "sesa_instnorm_stats: layout must be 0 or 1");
+  SESA_CHECK_ARG(batch > 0 && n1 > 0 && channels > 0 && n2 > 0, "sesa_instnorm_stats: empty tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  SESA_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)batch * channels, st));
+  const int64_t chunk = layout == 0 ? 128 : 4;
+  dim3 grid((unsigned)ceil_div64(n1, chunk), batch);
+  instnorm_acc_kernel<<<grid, 256, 0, st>>>(x, layout, batch, n1, channels, n2, ld, chunk, scratch);
+  SESA_LAUNCH_CHECK();
+  const int n = batch * channels;
+  instnorm_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(scratch, n, 1.0 / ((double)n1 * n2), eps,
+                                                            reinterpret_cast<float2*>(stats));
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+extern "C" int sesa_norm_act_split(const float* x, int mode, int batch, int64_t n1, int channels, int n2, int64_t ld,
+                                   const float* stats, const float* gamma, const float* beta, int act, void* planes,
+                                   int64_t ldp, int64_t p_plane, void* stream) {
+  SESA_CHECK_ARG(mode >= 0 && mode <= 2, "sesa_norm_act_split: mode must be 0, 1 or 2");
+  SESA_CHECK_ARG(stats == nullptr || (gamma != nullptr && beta != nullptr), "sesa_norm_act_split: stats need gamma and beta");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(planes);
+  const float2* s2 = reinterpret_cast<const float2*>(stats);
+  if (mode == 1) {
+    // n1 = T frames, n2 = F: x channels-last [b][t][f][c] -> planes [b][t][c][f]
+    const int64_t BT = (int64_t)batch * n1;
+    SESA_CHECK_ARG(BT <= 65535, "sesa_norm_act_split: too many (b, t) slices for one launch");
+    dim3 grid((channels + 31) / 32, (n2 + 31) / 32, (unsigned)BT);
+    norm_act_split_tr_kernel<<<grid, 256, 0, st>>>(x, BT, n2, channels, n1, ld, s2, gamma, beta, act, pl, ldp, p_plane);
+  } else {
+    const int inner = mode == 0 ? channels : n2;
+    SESA_CHECK_ARG((inner & 3) == 0 && (ldp & 3) == 0 && (p_plane & 3) == 0 && (mode != 0 || (ld & 3) == 0),
+                   "sesa_norm_act_split: inner extent and strides must be multiples of 4");
+    const int64_t rows = mode == 0 ? (int64_t)batch * n1 : (int64_t)batch * n1 * channels;
+    const int64_t total = rows * (inner >> 2);
+    norm_act_split_kernel<<<(unsigned)min((int64_t)148 * 16, ceil_div64(total, 256)), 256, 0, st>>>(
+        x, mode, rows, channels, n2, n1, ld, s2, gamma, beta, act, pl, ldp, p_plane);
+  }
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+extern "C" int sesa_transpose_add(float* x, const float* g, int64_t bt, int F, int channels, int64_t ld, void* stream) {
+  if (bt <= 0) return SESA_OK;
+  SESA_CHECK_ARG(bt <= 65535, "sesa_transpose_add: too many (b, t) slices for one launch");
+  dim3 grid((channels + 31) / 32, (F + 31) / 32, (unsigned)bt);
+  transpose_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, g, F, channels, ld);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+extern "C" int sesa_mdx_pack(const float* spec, int64_t bt, int f_full, int fs, int k, int c2, float* mix, void* stream) {
+  SESA_CHECK_ARG(k * fs <= f_full, "sesa_mdx_pack: dim_f exceeds the spectrogram");
+  const int64_t total = bt * fs * c2 * k;
+  if (total == 0) return SESA_OK;
+  mdx_pack_kernel<<<(unsigned)min((int64_t)148 * 16, ceil_div64(total, 256)), 256, 0, (cudaStream_t)stream>>>(spec, bt, f_full,
+                                                                                                           fs, k, c2, mix);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+extern "C" int sesa_mdx_final_concat(const float* mix, int ch, const float* x, int64_t ldx, const float* first, int64_t ldf,
+                                     int channels, int64_t rows, void* planes, int64_t ldp, int64_t p_plane, void* stream) {
+  const int64_t total = rows * (ch + channels);
+  if (total == 0) return SESA_OK;
+  mdx_final_concat_kernel<<<(unsigned)min((int64_t)148 * 16, ceil_div64(total, 256)), 256, 0, (cudaStream_t)stream>>>(
+      mix, ch, x, ldx, first, ldf, channels, rows, reinterpret_cast<__nv_bfloat16*>(planes), ldp, p_plane);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+extern "C" int sesa_mdx_unpack(const float* y, int64_t batch, int64_t frames, int fs, int k, int c2, int nt, int f_full,
+                               float* out, void* stream) {
+  const int64_t total = batch * nt * frames * f_full * c2;
+  if (total == 0) return SESA_OK;
+  mdx_unpack_kernel<<<(unsigned)min((int64_t)148 * 16, ceil_div64(total, 256)), 256, 0, (cudaStream_t)stream>>>(
+      y, batch, frames, fs, k, c2, nt, f_full, out);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}

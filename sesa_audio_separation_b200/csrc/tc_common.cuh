@@ -224,4 +224,4 @@ typedef CUresult (*sesa_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuui
 sesa_encode_tiled_fn sesa_get_encode_tiled();
 // bf16 tensor of `rank` dims (dims[0] innermost, strides_bytes[i] = byte stride of dim i+1), 128B-swizzled boxes.
 int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                        const uint64_t* strides_bytes, const uint32_t* box);
+                        const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);

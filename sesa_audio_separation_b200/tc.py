@@ -66,8 +66,22 @@ class TcGemmTable:
             w_ptr, ldw, w_pl = p['W']
             c_ptr, ldc = p.get('C') or (0, 0)
             p_ptr, ldp, p_pl = p.get('P') or (0, 0, 0)
-            arr[i] = (a_ptr, w_ptr, p.get('bias') or 0, p.get('rowscale') or 0, c_ptr, p_ptr, lda, a_pl, ldw, w_pl,
-                      ldc, ldp, p_pl, p['M'], p['N'], p['K'], 0)
+            rec = arr[i]
+            for name, val in (('A', a_ptr), ('W', w_ptr), ('bias', p.get('bias') or 0), ('rowscale', p.get('rowscale') or 0),
+                              ('C', c_ptr), ('P', p_ptr), ('lda', lda), ('a_plane', a_pl), ('ldw', ldw), ('w_plane', w_pl),
+                              ('ldc', ldc), ('ldp', ldp), ('p_plane', p_pl), ('M', p['M']), ('N', p['N']), ('K', p['K'])):
+                rec[name] = val
+            conv = p.get('conv')
+            if conv is not None:      # implicit-GEMM convolution: dict(cin, B, T, F, inT, inF, stride, taps=[(dt, df), ...])
+                taps = conv['taps']
+                rec['conv_taps'] = len(taps)
+                for name in ('cin', 'B', 'T', 'F', 'inT', 'inF', 'stride'):
+                    rec['conv_' + name] = conv[name]
+                rec['conv_dt'][:len(taps)] = [t[0] for t in taps]
+                rec['conv_df'][:len(taps)] = [t[1] for t in taps]
+            rm = p.get('row_map')
+            if rm is not None:        # (F_in, dt, df): 2x up-sampling scatter
+                rec['row_map'], rec['rm_F'], rec['rm_dt'], rec['rm_df'] = 1, rm[0], rm[1], rm[2]
         lib = _lib.load()
         nbytes = int(lib.sesa_gemm_tc_table_bytes(n))
         host = np.zeros(nbytes, dtype=np.uint8)

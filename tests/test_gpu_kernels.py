@@ -379,3 +379,120 @@ def test_attention_tc(lib, axis, B, T, F, nsplit):
     err = max_rel(ref.numpy(), got.numpy())
     print('attention_tc axis', axis, (B, T, F), 'nsplit', nsplit, 'max_rel', err)
     assert err < (3e-5 if nsplit == 3 else 1e-2)
+
+
+# ------------------------------------------------------------------ MDX23C building blocks
+def _cl_planes(lib, x):
+    """channels-last fp32 [B, T, F, C] on the device -> bf16 planes [2, B*T*F, round8(C)]"""
+    from sesa_audio_separation_b200 import tc
+    B, T, F, C = x.shape
+    pl = tc.alloc_planes(B * T * F, C, x.device)
+    lib.call('sesa_norm_act_split', P(x), 0, B, T * F, C, 1, C, None, None, None, 0, P(pl), pl.shape[-1], pl.stride(0), S())
+    return pl
+
+
+@pytest.mark.parametrize('B,T,F,cin,cout', [(2, 8, 128, 64, 96), (1, 16, 32, 24, 16), (2, 4, 256, 128, 256), (1, 8, 64, 16, 40)])
+def test_conv3x3_implicit_gemm(lib, B, T, F, cin, cout):
+    from sesa_audio_separation_b200 import tc
+    from sesa_audio_separation_b200._lib import GemmEpilogue
+    from sesa_audio_separation_b200.mdx23c import TAPS3, _r64
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, cin, T, F, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), padding=1).permute(0, 2, 3, 1)     # B T F cout
+    xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    pl = _cl_planes(lib, xd)
+    cp = _r64(cin)
+    wt = torch.zeros(cout, 9, cp)
+    wt[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    wp = tc.split_weight(wt.reshape(cout, 9 * cp).to(dev))
+    out = torch.zeros(B * T * F, cout, device=dev)
+    tab = tc.TcGemmTable([dict(A=tc.planes_arg(pl), W=tc.planes_arg(wp), M=B * T * F, N=cout, K=9 * cp, C=(out.data_ptr(), cout),
+                               conv=dict(cin=cin, B=B, T=T, F=F, inT=T, inF=F, stride=1, taps=TAPS3))], dev)
+    tab.run(GemmEpilogue(0, 0, 0, 0, 0, 0, 1, 1, None), nsplit=3)
+    torch.cuda.synchronize()
+    err = max_rel(ref.numpy(), out.cpu().reshape(B, T, F, cout).numpy())
+    print('conv3x3', (B, T, F, cin, cout), err)
+    assert err < 3e-5
+
+
+def test_downscale_and_upscale_convs(lib):
+    from sesa_audio_separation_b200 import tc
+    from sesa_audio_separation_b200._lib import GemmEpilogue
+    from sesa_audio_separation_b200.mdx23c import TAPS2, _r64
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(4)
+    B, T, F, cin, cout = 2, 8, 64, 48, 40
+    x = torch.randn(B, cin, T, F, generator=g)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    pl = _cl_planes(lib, xd)
+    ep = GemmEpilogue(0, 0, 0, 0, 0, 0, 1, 1, None)
+    # Conv2d(kernel = stride = 2)
+    w = torch.randn(cout, cin, 2, 2, generator=g) / math.sqrt(4 * cin)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), stride=2).permute(0, 2, 3, 1)
+    cp = _r64(cin)
+    wt = torch.zeros(cout, 4, cp)
+    wt[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 4, cin)
+    wp = tc.split_weight(wt.reshape(cout, 4 * cp).to(dev))
+    out = torch.zeros(B * (T // 2) * (F // 2), cout, device=dev)
+    tab = tc.TcGemmTable([dict(A=tc.planes_arg(pl), W=tc.planes_arg(wp), M=B * (T // 2) * (F // 2), N=cout, K=4 * cp,
+                               C=(out.data_ptr(), cout),
+                               conv=dict(cin=cin, B=B, T=T // 2, F=F // 2, inT=T, inF=F, stride=2, taps=TAPS2))], dev)
+    tab.run(ep, nsplit=3)
+    torch.cuda.synchronize()
+    assert max_rel(ref.numpy(), out.cpu().reshape(B, T // 2, F // 2, cout).numpy()) < 3e-5
+    # ConvTranspose2d(kernel = stride = 2), written into the first half of a concat buffer
+    wT = torch.randn(cin, cout, 2, 2, generator=g) / math.sqrt(cin)
+    refT = torch.nn.functional.conv_transpose2d(x.double(), wT.double(), stride=2).permute(0, 2, 3, 1)   # B 2T 2F cout
+    cat = torch.full((B * 2 * T * 2 * F, 2 * cout), 7.0, device=dev)
+    probs, keep = [], []
+    for (kh, kw) in TAPS2:
+        wpk = tc.split_weight(wT[:, :, kh, kw].t().contiguous().to(dev))
+        keep.append(wpk)
+        probs.append(dict(A=tc.planes_arg(pl), W=tc.planes_arg(wpk), M=B * T * F, N=cout, K=cin, C=(cat.data_ptr(), 2 * cout),
+                          row_map=(F, kh, kw)))
+    tc.TcGemmTable(probs, dev).run(ep, nsplit=3)
+    torch.cuda.synchronize()
+    got = cat.cpu().reshape(B, 2 * T, 2 * F, 2 * cout)
+    assert max_rel(refT.numpy(), got[..., :cout].numpy()) < 3e-5
+    assert torch.all(got[..., cout:] == 7.0)
+
+
+def test_instnorm_and_norm_act_split(lib):
+    from sesa_audio_separation_b200 import tc
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(6)
+    B, T, F, C = 2, 6, 40, 24
+    x = torch.randn(B, T, F, C, generator=g) * 2 + 0.7
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    xd, gd, bd = x.to(dev), gamma.to(dev), beta.to(dev)
+    scratch = torch.zeros(2 * B * C, device=dev, dtype=torch.float64)
+    stats = torch.zeros(B, C, 2, device=dev)
+    lib.call('sesa_instnorm_stats', P(xd), 0, B, T * F, C, 1, C, P(scratch), P(stats), 1e-5, S())
+    xn = torch.nn.functional.instance_norm(x.permute(0, 3, 1, 2).double(), weight=gamma.double(), bias=beta.double(), eps=1e-5)
+    ref = torch.nn.functional.gelu(xn).permute(0, 2, 3, 1)          # B T F C
+    pl = tc.alloc_planes(B * T * F, C, dev)
+    lib.call('sesa_norm_act_split', P(xd), 0, B, T * F, C, 1, C, P(stats), P(gd), P(bd), 1, P(pl), pl.shape[-1], pl.stride(0), S())
+    got = (pl[0].float() + pl[1].float()).cpu().reshape(B, T, F, C)
+    assert max_rel(ref.numpy(), got.numpy()) < 2e-5
+    # mode 1: channel-major planes [b][t][c][f]
+    pt = tc.alloc_planes(B * T * C, F, dev)
+    lib.call('sesa_norm_act_split', P(xd), 1, B, T, C, F, C, P(stats), P(gd), P(bd), 1, P(pt), pt.shape[-1], pt.stride(0), S())
+    gott = (pt[0].float() + pt[1].float()).cpu().reshape(B, T, C, F).permute(0, 1, 3, 2)
+    assert max_rel(ref.numpy(), gott.numpy()) < 2e-5
+    # layout 1 statistics + mode 2 on channel-major data
+    xc = x.permute(0, 1, 3, 2).contiguous().to(dev)                  # B T C F
+    stats2 = torch.zeros(B, C, 2, device=dev)
+    lib.call('sesa_instnorm_stats', P(xc), 1, B, T, C, F, 0, P(scratch), P(stats2), 1e-5, S())
+    assert max_rel(stats.cpu().numpy(), stats2.cpu().numpy()) < 1e-5
+    pc = tc.alloc_planes(B * T * C, F, dev)
+    lib.call('sesa_norm_act_split', P(xc), 2, B, T, C, F, 0, P(stats2), P(gd), P(bd), 1, P(pc), pc.shape[-1], pc.stride(0), S())
+    gotc = (pc[0].float() + pc[1].float()).cpu().reshape(B, T, C, F).permute(0, 1, 3, 2)
+    assert max_rel(ref.numpy(), gotc.numpy()) < 2e-5
+    # transpose-add
+    gq = torch.randn(B * T, C, F, generator=g)
+    x2 = xd.clone()
+    gqd = gq.to(dev)
+    lib.call('sesa_transpose_add', P(x2), P(gqd), B * T, F, C, C, S())
+    assert torch.allclose(x2.cpu(), x + gq.reshape(B, T, C, F).permute(0, 1, 3, 2))

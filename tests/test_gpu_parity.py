@@ -33,7 +33,7 @@ def build(case):
     return m.eval().to('cuda'), sd
 
 
-@pytest.mark.parametrize('name', [n for n in CASES if CASES[n]['kind'] != 'mdx23c'])
+@pytest.mark.parametrize('name', list(CASES))
 def test_forward_matches_reference_golden(manifest, name):
     case = CASES[name]
     model, sd = build(case)
