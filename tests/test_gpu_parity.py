@@ -127,3 +127,28 @@ def test_full_size_bs_roformer_chunk_vs_oracle_on_gpu():
     print('full-size BS chunk: max_rel', max_rel(ref, y), 'snr', snr_db(ref, y))
     assert max_rel(ref, y) <= FP32_MAX_REL
     assert snr_db(ref, y) >= FP32_SNR_DB
+
+
+def test_full_size_mdx23c_chunk_vs_oracle_on_gpu():
+    """BASELINE C1 model (MDX23C vocals, 112 M parameters) on one full 261120-sample chunk against the oracle
+    restatement evaluated in true fp32 on the same GPU (TF32 off)."""
+    import os
+    import sesa_audio_separation_b200 as sesa
+    from conftest import ROOT
+    from oracle import mdx23c as omdx
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model, cfg = sesa.get_model_from_config('mdx23c', os.path.join(ROOT, 'configs', 'config_vocals_mdx23c.yaml'))
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=21)
+    model.load_state_dict(sd)
+    model.eval().to('cuda')
+    x = torch.from_numpy(synth_mix(261120, 2, seed=22))[None].cuda()
+    y = model(x).cpu().numpy()
+    ocfg = dict(audio=dict(cfg.audio), model=dict(cfg.model), num_target_instruments=2)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    with torch.inference_mode():
+        ref = omdx.mdx23c_forward(sd_gpu, ocfg, x).cpu().numpy()
+    print('full-size MDX23C chunk: max_rel', max_rel(ref, y), 'snr', snr_db(ref, y))
+    assert y.shape == ref.shape == (1, 2, 2, 261120)
+    assert max_rel(ref, y) <= FP32_MAX_REL
+    assert snr_db(ref, y) >= FP32_SNR_DB

@@ -106,3 +106,18 @@ def test_config_loading_with_python_tuple(tmp_path):
     assert sesa.prefer_target_instrument(cfg) == ['vocals']
     with pytest.raises(ValueError):
         sesa.get_model_from_config('scnet', str(p))
+
+
+def test_benchmark_yaml_configs_load_and_build():
+    """configs/*.yaml (BASELINE configs 1-3) load through the reference-style registry and give the reference's
+    parameter counts (SURVEY section 6 probes: BS 159.76 M, MDX23C 111.99 M, Mel 4-stem 832.6 M)."""
+    import sesa_audio_separation_b200 as sesa
+    want = {'bs_roformer': ('config_bs_roformer_vocals.yaml', 159_758_796, ['vocals']),
+            'mel_band_roformer': ('config_mel_band_roformer_4stem.yaml', 832_599_084, ['bass', 'drums', 'other', 'vocals']),
+            'mdx23c': ('config_vocals_mdx23c.yaml', 111_990_272, ['vocals', 'other'])}
+    for mt, (fn, n, inst) in want.items():
+        model, cfg = sesa.get_model_from_config(mt, os.path.join(ROOT, 'configs', fn))
+        assert sum(v.numel() for v in model.state_dict().values()) == n
+        assert list(sesa.prefer_target_instrument(cfg)) == inst
+    with pytest.raises(ValueError):
+        sesa.get_model_from_config('scnet', os.path.join(ROOT, 'configs', 'config_vocals_mdx23c.yaml'))
