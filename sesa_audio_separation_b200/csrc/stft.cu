@@ -222,7 +222,10 @@ extern "C" int sesa_mask_istft(const float* spec, const float* mask, const int* 
   SESA_CHECK_ARG(out_len > 0 && out_len <= (int64_t)hop * (n_frames - 1) + n_fft / 2,
                  "sesa_mask_istft: out_len %lld not covered by %d frames", (long long)out_len, n_frames);
   if (batch == 0 || nstems == 0) return SESA_OK;
-  int groups_of = 12;  // frames' worth of hops per CTA: (G+4)/G redundant transforms
+  int groups_of = 12;  // frames' worth of hops per CTA: (G + n_fft/hop - 1)/G redundant transforms
+  while (groups_of > 1 &&
+         (size_t)2 * n_fft * sizeof(float2) + (size_t)channels * groups_of * hop * sizeof(float) > 200 * 1024)
+    --groups_of;   // n_fft 8192 / hop 1024 (MDX23C): 128 KB of FFT buffers leave room for 8 hops
   int seg = groups_of * hop;
   const int ngroups = (int)ceil_div64(out_len, seg);
   const size_t smem = (size_t)2 * n_fft * sizeof(float2) + (size_t)channels * seg * sizeof(float);
