@@ -140,11 +140,13 @@ int sesa_gemm_tc(const void* table_dev, int n_groups, int total_tiles, int block
 /* Tensor-core attention (attend.py:89-93; gating and head merge bs_roformer.py:115-120).  qkv_planes: bf16
  * [planes][rows][ld] with row layout [q(h d) | k(h d) | v(h d)] (q pre-scaled, q/k rotated); gates: fp32 logits
  * [rows][ldg]; out_planes: bf16 [out_planes][rows][ldo] = softmax(q k^T) v * sigmoid(gate), heads merged.
- * Sequence geometry as sesa_attention_simt.  Short contiguous sequences (seq_len <= 64) are packed per tile. */
+ * Sequence geometry as sesa_attention_simt.  Short contiguous sequences (seq_len <= 64) are packed per tile; they are
+ * packed within groups of seq_group consecutive sequences (0 = all), so that with seq_group = frames per chunk a
+ * chunk's result does not depend on the batch it is launched in. */
 int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t plane_stride, const float* gates, int64_t ldg,
                       void* out_planes_ptr, int64_t ldo, int64_t out_plane_stride, int heads, int dim_head, int n_seq,
                       int seq_len, int inner_cnt, int64_t outer_stride, int64_t inner_stride, int64_t pos_stride,
-                      int nsplit, int out_planes, void* stream);
+                      int seq_group, int nsplit, int out_planes, void* stream);
 /* Row preparation for the tensor-core GEMMs: per row r of x[rows][dim] (row stride ldx)
  *   inv = normalize ? 1/max(||x_r||_2, 1e-12) : 1                 (F.normalize of RMSNorm, bs_roformer.py:49)
  *   planes[p][r][:] = bf16 split of x_r * inv                      (p < out_planes, row stride ldp)

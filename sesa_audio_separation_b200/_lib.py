@@ -60,7 +60,7 @@ _SIGS = {
     'sesa_gemm_tc_build': (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_int)]),
     'sesa_gemm_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(GemmEpilogue), c_void_p]),
     'sesa_attention_tc': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
-                                  c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+                                  c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     'sesa_prep_rows': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_int64, c_int,
                                c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     'sesa_split_weight': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),

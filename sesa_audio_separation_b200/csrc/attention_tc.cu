@@ -38,6 +38,8 @@ struct AttnParams {
   int inner_cnt;        // strided: sequence s -> (b = s / inner_cnt, f = s % inner_cnt)
   int64_t outer_stride, inner_stride, pos_stride;  // strided: row = b*outer + f*inner + pos*pos_stride
   int spt;              // packed: sequences per tile
+  int seq_group;        // packed: sequences are packed within groups of this many (one group per chunk), so a
+  int tiles_per_group;  //         sequence's arithmetic never depends on the batch it is launched in
   int out_planes;
 };
 
@@ -119,7 +121,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
     c3 = seq / p.inner_cnt;
     nblk = (p.seq_len + BKV - 1) / BKV;
   } else {
-    row_base = (int64_t)blockIdx.x * p.spt * p.seq_len;
+    const int grp = blockIdx.x / p.tiles_per_group;
+    const int lt = blockIdx.x - grp * p.tiles_per_group;
+    row_base = ((int64_t)grp * p.seq_group + (int64_t)lt * p.spt) * p.seq_len;
     nblk = BQ / BKV;
   }
 
@@ -224,8 +228,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       out_row = (int64_t)c3 * p.outer_stride + (int64_t)c1 * p.inner_stride + (int64_t)(q0 + i) * p.pos_stride;
     } else {
       const int sl = i / p.seq_len;
-      const int64_t gseq = (int64_t)blockIdx.x * p.spt + sl;
-      row_valid = sl < p.spt && gseq < p.n_seq;
+      const int grp = blockIdx.x / p.tiles_per_group;
+      const int lseq = (blockIdx.x - grp * p.tiles_per_group) * p.spt + sl;   // sequence index inside its group
+      row_valid = sl < p.spt && lseq < p.seq_group && (int64_t)grp * p.seq_group + lseq < p.n_seq;
       lo = row_valid ? sl * p.seq_len : 0;
       hi = row_valid ? lo + p.seq_len : 0;
       out_row = row_base + i;
@@ -344,7 +349,8 @@ int launch_attention_tc(const CUtensorMap& map, const AttnParams& p, dim3 grid, 
 extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t plane_stride, const float* gates,
                                  int64_t ldg, void* out_planes_ptr, int64_t ldo, int64_t out_plane_stride, int heads,
                                  int dim_head, int n_seq, int seq_len, int inner_cnt, int64_t outer_stride,
-                                 int64_t inner_stride, int64_t pos_stride, int nsplit, int out_planes, void* stream) {
+                                 int64_t inner_stride, int64_t pos_stride, int seq_group, int nsplit, int out_planes,
+                                 void* stream) {
   SESA_CHECK_ARG(dim_head == DH, "sesa_attention_tc: dim_head must be 64, got %d", dim_head);
   SESA_CHECK_ARG((ld & 7) == 0 && (ldo & 7) == 0 && (plane_stride & 7) == 0 && (out_plane_stride & 7) == 0,
                  "sesa_attention_tc: plane strides must be multiples of 8 bf16 elements");
@@ -371,6 +377,8 @@ extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t pla
   p.pos_stride = pos_stride;
   p.out_planes = out_planes;
   p.spt = 1;
+  p.seq_group = n_seq;
+  p.tiles_per_group = 1;
   CUtensorMap map;
   dim3 grid;
   const bool packed = pos_stride == 1 && seq_len <= BKV && inner_cnt == 1 && outer_stride == seq_len;
@@ -379,13 +387,16 @@ extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t pla
     // rows are one contiguous run of n_seq*seq_len tokens
     p.mode = 1;
     p.spt = BQ / seq_len;
+    p.seq_group = seq_group > 0 ? seq_group : n_seq;
+    SESA_CHECK_ARG(n_seq % p.seq_group == 0, "sesa_attention_tc: n_seq must be a multiple of seq_group");
+    p.tiles_per_group = (p.seq_group + p.spt - 1) / p.spt;
     const uint64_t rows = (uint64_t)n_seq * seq_len;
     const uint64_t dims[5] = {(uint64_t)3 * inner, rows, 1, 1, 2};
     const uint64_t str[4] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * rows, (uint64_t)ld * 2 * rows, (uint64_t)plane_stride * 2};
     const uint32_t boxp[5] = {64, 64, 1, 1, 1};
     int rc = sesa_make_tmap_bf16(&map, qkv_planes, 5, dims, str, boxp);
     if (rc != SESA_OK) return rc;
-    grid = dim3((unsigned)((n_seq + p.spt - 1) / p.spt), 1, heads);
+    grid = dim3((unsigned)((n_seq / p.seq_group) * p.tiles_per_group), 1, heads);
   } else {
     // sequence s = (b, f): row = b*outer + f*inner + pos*pos_stride
     p.mode = 0;

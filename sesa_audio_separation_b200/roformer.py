@@ -419,7 +419,7 @@ class _RoformerBase(KernelModule):
                 qp, ap = ws['qkvp'], ws['aop']
                 call('sesa_attention_tc', _ptr(qp), qp.shape[-1], qp.stride(0), _ptr(ws['gates']), 8, _ptr(ap),
                      ap.shape[-1], ap.stride(0), H, self.dim_head, n_seq, seq_len, inner_cnt, outer, inner_s, pos_s,
-                     nsplit, 2, _stream())
+                     T if axis == 1 else 0, nsplit, 2, _stream())
                 t['out'].run(_epilogue(residual=1), nsplit)
                 tc.prep_rows(ws['x'], M, D, D, ws['xp'], True)
                 t['ff1'].run(_epilogue(act=_lib.ACT_GELU), nsplit)

@@ -360,7 +360,7 @@ def test_attention_tc(lib, axis, B, T, F, nsplit):
     else:
         args = (B * T, F, 1, F, 0, 1)
     lib.call('sesa_attention_tc', P(planes), planes.shape[-1], planes.stride(0), P(gd), 8, P(out), out.shape[-1],
-             out.stride(0), H, dh, *args, nsplit, 2, S())
+             out.stride(0), H, dh, *args, T if axis == 1 else 0, nsplit, 2, S())
     torch.cuda.synchronize()
     src = qkv if nsplit == 3 else planes[0].float().cpu()
     x = src.reshape(B, T, F, 3 * inner).double()

@@ -152,3 +152,17 @@ def test_full_size_mdx23c_chunk_vs_oracle_on_gpu():
     assert y.shape == ref.shape == (1, 2, 2, 261120)
     assert max_rel(ref, y) <= FP32_MAX_REL
     assert snr_db(ref, y) >= FP32_SNR_DB
+
+
+@pytest.mark.parametrize('name', ['bs_small', 'mel_small'])
+def test_forward_is_batch_invariant(name):
+    """A chunk's output must not depend on the batch it is launched in (engine_batch is a throughput knob only, and
+    chunk-range sharding across GPUs regroups chunks): bitwise equality of batched vs one-by-one forwards."""
+    case = CASES[name]
+    model, _ = build(case)
+    x = make_input(case).cuda()
+    x = torch.cat([x, x.flip(0) * 0.5, x * 0.25], 0)
+    y = model(x).clone()
+    for i in range(x.shape[0]):
+        yi = model(x[i:i + 1])
+        assert torch.equal(yi[0], y[i]), (name, i, float((yi[0] - y[i]).abs().max()))

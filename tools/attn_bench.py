@@ -37,7 +37,7 @@ def main():
             continue
         def run():
             _lib.call('sesa_attention_tc', P(planes), planes.shape[-1], planes.stride(0), P(gates), 8, P(out),
-                      out.shape[-1], out.stride(0), H, dh, *a, args.nsplit, 2, st)
+                      out.shape[-1], out.stride(0), H, dh, *a, T if name == 'band' else 0, args.nsplit, 2, st)
         for _ in range(2):
             run()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
