@@ -123,6 +123,16 @@ typedef struct sesa_tc_problem {
   /* Output row remap: 0 = row m; 1 = 2x up-sampling scatter of nn.ConvTranspose2d(kernel = stride = 2)
    * (mdx23c_tfc_tdf_v3.py:80): row = (2*(m / rm_F) + rm_dt) * 2*rm_F + 2*(m % rm_F) + rm_df. */
   int32_t row_map, rm_F, rm_dt, rm_df;
+  /* Fused RMSNorm bookkeeping (bs_roformer.py:43-50 applied to the residual stream without a separate pass):
+   * ss_out (producer, optional): ss_out[row * 2*ceil(N/block_n) + slot] receives this launch's per-row partial sums of
+   *   squares of the stored values, one slot per (column block, column half) — deterministic, no atomics;
+   * rowss (consumer, optional): acc[m,:] *= 1 / max(sqrt(sum_k rowss[m*ss_slots + k]), 1e-12). */
+  const float* rowss;
+  float* ss_out;
+  int32_t ss_slots;
+  int32_t p_cols;   /* planes P are written for columns n < p_cols (0 = all columns) */
+  int32_t c_col0;   /* C is written for columns n >= c_col0, at column n - c_col0 (to_gates logits next to to_qkv) */
+  int32_t _pad2;
 } sesa_tc_problem;
 
 /* Bytes of the device-side group table for n_groups problems. */
@@ -148,13 +158,15 @@ int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t plane_stride, 
                       int seq_len, int inner_cnt, int64_t outer_stride, int64_t inner_stride, int64_t pos_stride,
                       int seq_group, int nsplit, int out_planes, void* stream);
 /* Row preparation for the tensor-core GEMMs: per row r of x[rows][dim] (row stride ldx)
- *   inv = normalize ? 1/max(||x_r||_2, 1e-12) : 1                 (F.normalize of RMSNorm, bs_roformer.py:49)
+ *   inv = normalize == 1 ? 1/max(||x_r||_2, 1e-12) : 1            (F.normalize of RMSNorm, bs_roformer.py:49)
  *   planes[p][r][:] = bf16 split of x_r * inv                      (p < out_planes, row stride ldp)
  *   gates[r][h] = (x_r * inv) . gate_w[h] + gate_b[h], h < n_gates (to_gates logits, bs_roformer.py:117; optional)
- *   rowinv[r] = inv                                                (optional) */
+ *   rowinv[r] = inv                                                (optional; normalize == 2: planes stay
+ *                                                                   un-normalised and rowinv[r*ss_slots + 0] = ||x_r||^2,
+ *                                                                   slots 1.. = 0: the rowss input of sesa_gemm_tc) */
 int sesa_prep_rows(const float* x, int64_t ldx, int64_t rows, int dim, int normalize, void* planes, int64_t ldp,
                    int64_t p_plane, int out_planes, const float* gate_w, const float* gate_b, int n_gates,
-                   float* gates, int64_t ldg, float* rowinv, void* stream);
+                   float* gates, int64_t ldg, float* rowinv, int ss_slots, void* stream);
 /* bf16 hi/lo planes of a weight matrix w[rows][cols] -> planes[2][rows][ldp] (zero padded to ldp). */
 int sesa_split_weight(const float* w, int64_t rows, int64_t cols, void* planes, int64_t ldp, void* stream);
 

@@ -31,7 +31,7 @@ GEMM_GROUP_DTYPE = np.dtype([('A', '<u8'), ('W', '<u8'), ('bias', '<u8'), ('C', 
                              ('lda', '<i8'), ('ldw', '<i8'), ('ldc', '<i8')])
 assert GEMM_GROUP_DTYPE.itemsize == 72
 
-# numpy mirror of struct sesa_tc_problem (240 bytes)
+# numpy mirror of struct sesa_tc_problem (272 bytes)
 TC_PROBLEM_DTYPE = np.dtype([('A', '<u8'), ('W', '<u8'), ('bias', '<u8'), ('rowscale', '<u8'), ('C', '<u8'),
                              ('P', '<u8'), ('lda', '<i8'), ('a_plane', '<i8'), ('ldw', '<i8'), ('w_plane', '<i8'),
                              ('ldc', '<i8'), ('ldp', '<i8'), ('p_plane', '<i8'),
@@ -39,8 +39,10 @@ TC_PROBLEM_DTYPE = np.dtype([('A', '<u8'), ('W', '<u8'), ('bias', '<u8'), ('rows
                              ('conv_taps', '<i4'), ('conv_cin', '<i4'), ('conv_B', '<i4'), ('conv_T', '<i4'),
                              ('conv_F', '<i4'), ('conv_inT', '<i4'), ('conv_inF', '<i4'), ('conv_stride', '<i4'),
                              ('conv_dt', '<i4', (9,)), ('conv_df', '<i4', (9,)),
-                             ('row_map', '<i4'), ('rm_F', '<i4'), ('rm_dt', '<i4'), ('rm_df', '<i4')])
-assert TC_PROBLEM_DTYPE.itemsize == 240
+                             ('row_map', '<i4'), ('rm_F', '<i4'), ('rm_dt', '<i4'), ('rm_df', '<i4'),
+                             ('rowss', '<u8'), ('ss_out', '<u8'), ('ss_slots', '<i4'), ('p_cols', '<i4'),
+                             ('c_col0', '<i4'), ('_pad2', '<i4')])
+assert TC_PROBLEM_DTYPE.itemsize == 272
 
 _SIGS = {
     'sesa_abi_version': (c_int, []),
@@ -62,7 +64,7 @@ _SIGS = {
     'sesa_attention_tc': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
                                   c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     'sesa_prep_rows': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_int64, c_int,
-                               c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+                               c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     'sesa_split_weight': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     'sesa_rmsnorm': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'sesa_add_inplace': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

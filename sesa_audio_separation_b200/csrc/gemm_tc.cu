@@ -42,6 +42,13 @@ struct alignas(128) TcGroup {
   int32_t taps, kb_per_tap, conv_T, conv_F, conv_stride;
   int32_t row_map, rm_F, rm_dt, rm_df;
   int32_t tap_dt[9], tap_df[9];
+  // fused RMSNorm bookkeeping: per-row partial sums of squares, one slot per (n-block, column half) of the producer
+  const float* rowss;   // consumer: rs = 1 / max(sqrt(sum of ss_slots partials), 1e-12)
+  float* ss_out;        // producer: ss_out[row * (2*n_blocks) + 2*nb + half] = sum of squares of the stored values
+  int32_t ss_slots;     // slots per row in rowss
+  int32_t p_cols;       // planes are written for columns < p_cols (0 = all)
+  int32_t c_col0;       // C is written for columns >= c_col0, at column n - c_col0
+  int32_t _r2;
 };
 static_assert(sizeof(TcGroup) % 128 == 0, "table entries must keep the tensor maps 128-byte aligned");
 
@@ -194,7 +201,6 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN, 0, 0);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -202,6 +208,10 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
         const int kbs = g->k_blocks;
+        // the last column block of a problem only multiplies the columns that exist (N granularity 16)
+        const int n_left = g->N - ((tile - g->tile_begin) % g->n_blocks) * BN;
+        const int n_eff = n_left >= BN ? BN : ((n_left + 15) & ~15);
+        const uint32_t idesc = tc::make_idesc_bf16(BM, n_eff, 0, 0);
         tc::mbar_wait(&tmem_empty[as], aph ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -254,7 +264,16 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       float* __restrict__ Cp = g->C;
       __nv_bfloat16* __restrict__ Pp = g->P;
       const int64_t ldc = g->ldc, ldp = g->ldp, p_plane = g->p_plane;
-      const float rs = (g->rowscale != nullptr && row_ok) ? g->rowscale[m] : 1.0f;
+      float rs = (g->rowscale != nullptr && row_ok) ? g->rowscale[m] : 1.0f;
+      if (g->rowss != nullptr && row_ok) {   // fused RMSNorm: F.normalize(x, dim=-1) of the GEMM input (bs_roformer.py:49)
+        float ssum = 0.f;
+        for (int k = 0; k < g->ss_slots; ++k) ssum += g->rowss[(int64_t)m * g->ss_slots + k];
+        rs = 1.0f / fmaxf(sqrtf(ssum), 1e-12f);
+      }
+      float* __restrict__ ss_out = g->ss_out;
+      const int p_cols = g->p_cols > 0 ? g->p_cols : N;
+      const int c_col0 = g->c_col0;
+      float ssq[4] = {0.f, 0.f, 0.f, 0.f};
       int pos = 0;
       if ((FLAVOR == F_ROT || FLAVOR == F_GENERIC) && ep.rot_cols > 0) pos = (m / ep.pos_div) % ep.pos_mod;
       const int row_map = g->row_map, rm_F = g->rm_F, rm_dt = g->rm_dt, rm_df = g->rm_df;
@@ -356,8 +375,9 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             const int64_t orow = out_row(mm);
             if (colb + 3 < N) {
               if (ep.residual) { o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w; }
-              if (Cp != nullptr) *reinterpret_cast<float4*>(Cp + orow * ldc + colb) = o;
-              if (Pp != nullptr) {
+              ssq[it] += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+              if (Cp != nullptr && colb >= c_col0) *reinterpret_cast<float4*>(Cp + orow * ldc + (colb - c_col0)) = o;
+              if (Pp != nullptr && colb < p_cols) {
                 __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
                 tc::split_bf16(o.x, h0, l0); tc::split_bf16(o.y, h1, l1);
                 tc::split_bf16(o.z, h2, l2); tc::split_bf16(o.w, h3, l3);
@@ -369,12 +389,13 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               const float ov[4] = {o.x, o.y, o.z, o.w};
               for (int e = 0; e < 4 && colb + e < N; ++e) {
                 float val = ov[e];
-                if (Cp != nullptr) {
-                  float* cp = Cp + orow * ldc + colb + e;
+                if (Cp != nullptr && colb + e >= c_col0) {
+                  float* cp = Cp + orow * ldc + colb + e - c_col0;
                   if (ep.residual) val += *cp;
                   *cp = val;
                 }
-                if (Pp != nullptr) {
+                ssq[it] += val * val;
+                if (Pp != nullptr && colb + e < p_cols) {
                   __nv_bfloat16 h, l;
                   tc::split_bf16(val, h, l);
                   Pp[orow * ldp + colb + e] = h;
@@ -416,6 +437,17 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
+      if (ss_out != nullptr) {   // this warp's slot of the row sums of squares (rows it*8 + lane/4, 4 lanes per row)
+        const int slots = 2 * g->n_blocks;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float v = ssq[it];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          const int mm = m_base + it * 8 + (lane >> 2);
+          if ((lane & 3) == 0 && mm < M) ss_out[out_row(mm) * slots + 2 * nb + ch] = v;
+        }
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
@@ -580,6 +612,16 @@ extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int b
     if (rc != SESA_OK) return rc;
     g.bias = p.bias;
     g.rowscale = p.rowscale;
+    g.rowss = p.rowss;
+    g.ss_out = p.ss_out;
+    g.ss_slots = p.ss_slots;
+    g.p_cols = p.p_cols;
+    g.c_col0 = p.c_col0;
+    SESA_CHECK_ARG(p.rowss == nullptr || (p.ss_slots > 0 && p.ss_slots <= 16), "sesa_gemm_tc_build: problem %d: bad ss_slots", i);
+    SESA_CHECK_ARG(p.ss_out == nullptr || (p.C == nullptr || ((p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0)),
+                   "sesa_gemm_tc_build: problem %d: ss_out needs 16-byte aligned fp32 output rows", i);
+    SESA_CHECK_ARG(p.c_col0 >= 0 && (p.c_col0 & 3) == 0 && p.p_cols >= 0 && (p.p_cols & 3) == 0,
+                   "sesa_gemm_tc_build: problem %d: p_cols / c_col0 must be multiples of 4", i);
     g.C = p.C;
     g.P = reinterpret_cast<__nv_bfloat16*>(p.P);
     g.ldc = p.ldc;
@@ -629,7 +671,7 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict_
                                                         const float* __restrict__ gate_w,
                                                         const float* __restrict__ gate_b, int n_gates,
                                                         float* __restrict__ gates, int64_t ldg,
-                                                        float* __restrict__ rowinv) {
+                                                        float* __restrict__ rowinv, int ss_slots) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -644,9 +686,13 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict_
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (normalize == 2) {   // planes stay raw; hand the sum of squares to the consuming GEMM (slot 0, others 0)
+      if (rowinv != nullptr && lane < ss_slots) rowinv[row * ss_slots + lane] = lane == 0 ? ss : 0.f;
+    } else {
+      inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    }
   }
-  if (rowinv != nullptr && lane == 0) rowinv[row] = inv;
+  if (rowinv != nullptr && normalize != 2 && lane == 0) rowinv[row] = inv;
   float gacc[8];
 #pragma unroll
   for (int h = 0; h < 8; ++h) gacc[h] = 0.f;
@@ -684,17 +730,19 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const float* __restrict_
 
 extern "C" int sesa_prep_rows(const float* x, int64_t ldx, int64_t rows, int dim, int normalize, void* planes,
                               int64_t ldp, int64_t p_plane, int out_planes, const float* gate_w, const float* gate_b,
-                              int n_gates, float* gates, int64_t ldg, float* rowinv, void* stream) {
+                              int n_gates, float* gates, int64_t ldg, float* rowinv, int ss_slots, void* stream) {
   SESA_CHECK_ARG(dim > 0 && (dim & 3) == 0 && (ldx & 3) == 0, "sesa_prep_rows: dim and ldx must be multiples of 4");
   SESA_CHECK_ARG(planes == nullptr || ((ldp & 3) == 0 && (p_plane & 3) == 0), "sesa_prep_rows: plane strides must be multiples of 4");
   SESA_CHECK_ARG(n_gates >= 0 && n_gates <= 8, "sesa_prep_rows: at most 8 gate outputs");
   SESA_CHECK_ARG(n_gates == 0 || (gate_w != nullptr && gates != nullptr), "sesa_prep_rows: gates need weights and an output");
   SESA_CHECK_ARG(out_planes == 1 || out_planes == 2, "sesa_prep_rows: out_planes must be 1 or 2");
+  SESA_CHECK_ARG(normalize >= 0 && normalize <= 2 && (normalize != 2 || (ss_slots >= 1 && ss_slots <= 32)),
+                 "sesa_prep_rows: normalize must be 0, 1 or 2 (with 1 <= ss_slots <= 32)");
   if (rows <= 0) return SESA_OK;
   const int wpb = 8;
   prep_rows_kernel<<<(unsigned)ceil_div64(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       x, ldx, rows, dim, normalize, reinterpret_cast<__nv_bfloat16*>(planes), ldp, p_plane, out_planes, gate_w, gate_b,
-      n_gates, gates, ldg, rowinv);
+      n_gates, gates, ldg, rowinv, ss_slots);
   SESA_LAUNCH_CHECK();
   return SESA_OK;
 }

@@ -99,6 +99,8 @@ class _RoformerBase(KernelModule):
             raise NotImplementedError('stft_win_length != stft_n_fft is not supported')
         if dim_head != 64:
             raise NotImplementedError('the attention kernels are built for dim_head == 64')
+        if heads > 8:
+            raise NotImplementedError('the engine supports at most 8 attention heads (gate logits are stored 8 per token)')
         self.dim, self.depth, self.stereo = dim, depth, stereo
         self.audio_channels = 2 if stereo else 1
         self.num_stems = num_stems
@@ -198,8 +200,9 @@ class _RoformerBase(KernelModule):
                         w2=P[p + '1.net.4.weight'].contiguous(), b2=P[p + '1.net.4.bias'].contiguous(),
                         freqs=P[p + '0.rotary_embed.freqs'].float().cpu())
                     if self._tc:   # bf16 hi/lo planes of the folded weights for the tcgen05 GEMMs
-                        sub.update(wqkv_p=tc.split_weight(w[:3 * inner]), gate_w=w[3 * inner:3 * inner + H].contiguous(),
-                                   gate_b=bias[3 * inner:3 * inner + H].contiguous(), wo_p=tc.split_weight(sub['wo']),
+                        # to_qkv and to_gates share one GEMM: rows [q | k | v | gate logits]
+                        sub.update(wqkv_p=tc.split_weight(w[:3 * inner + H]), bqkvg=bias[:3 * inner + H].contiguous(),
+                                   wo_p=tc.split_weight(sub['wo']),
                                    w1_p=tc.split_weight(sub['w1']), w2_p=tc.split_weight(sub['w2']))
                     subs.append(sub)
                 norm = P[f'layers.{i}.{a}.norm.gamma'].contiguous() if self.norm_output else None
@@ -343,22 +346,30 @@ class _RoformerBase(KernelModule):
         ws['qkvp'] = tc.alloc_planes(M, 3 * inner, dev)  # rotated q (pre-scaled) | rotated k | v
         ws['gates'] = torch.zeros(M, 8, device=dev, dtype=torch.float32)   # to_gates logits
         x = ws['x']
+        # per-row partial sums of squares of the residual stream, written by the residual GEMM epilogues (one slot per
+        # column block and half) and consumed as the fused RMSNorm row scale of the next GEMM
+        slots = 2 * ((D + 255) // 256)
+        ws['ss_slots'] = slots
+        ws['ss'] = torch.zeros(M, slots, device=dev, dtype=torch.float32)
+        ss_ptr = ws['ss'].data_ptr()
 
-        def one(A, Wp, Mm, N, K, bias=None, C=None, Pl=None):
+        def one(A, Wp, Mm, N, K, bias=None, C=None, Pl=None, **extra):
             return tc.TcGemmTable([dict(A=tc.planes_arg(A), W=tc.planes_arg(Wp), M=Mm, N=N, K=K,
                                         bias=bias.data_ptr() if bias is not None else 0,
                                         C=(C.data_ptr(), C.shape[-1]) if C is not None else None,
-                                        P=tc.planes_arg(Pl) if Pl is not None else None)], dev)
+                                        P=tc.planes_arg(Pl) if Pl is not None else None, **extra)], dev)
         ws['t_layers'] = []
         for pair in prep['layers']:
             gp = []
             for tr in pair:
                 gs = []
                 for s in tr['subs']:
-                    gs.append(dict(qkv=one(ws['xp'], s['wqkv_p'], M, 3 * inner, D, Pl=ws['qkvp']),
-                                   out=one(ws['aop'], s['wo_p'], M, D, inner, C=x),
-                                   ff1=one(ws['xp'], s['w1_p'], M, 4 * D, D, bias=s['b1'], Pl=ws['hp']),
-                                   ff2=one(ws['hp'], s['w2_p'], M, D, 4 * D, bias=s['b2'], C=x)))
+                    gs.append(dict(
+                        qkv=one(ws['xp'], s['wqkv_p'], M, 3 * inner + self.heads, D, bias=s['bqkvg'], C=ws['gates'],
+                                Pl=ws['qkvp'], rowss=ss_ptr, ss_slots=slots, p_cols=3 * inner, c_col0=3 * inner),
+                        out=one(ws['aop'], s['wo_p'], M, D, inner, C=x, Pl=ws['xp'], ss_out=ss_ptr),
+                        ff1=one(ws['xp'], s['w1_p'], M, 4 * D, D, bias=s['b1'], Pl=ws['hp'], rowss=ss_ptr, ss_slots=slots),
+                        ff2=one(ws['hp'], s['w2_p'], M, D, 4 * D, bias=s['b2'], C=x, Pl=ws['xp'], ss_out=ss_ptr)))
                 gp.append(gs)
             ws['t_layers'].append(gp)
         # mask estimators: grouped over (stem, band)
@@ -397,6 +408,10 @@ class _RoformerBase(KernelModule):
     def _gemm(self, table, ep):
         call('sesa_gemm_simt', _ptr(table.dev), table.n, table.max_m, table.max_n, ctypes.byref(ep), _stream())
 
+    def _refresh_planes(self, ws):
+        """(Re)build the bf16 planes and row sums of squares of the residual stream after a non-GEMM producer."""
+        tc.prep_rows(ws['x'], ws['M'], self.dim, self.dim, ws['xp'], 2, rowinv=ws['ss'], ss_slots=ws['ss_slots'])
+
     def _transformer(self, ws, prep, gl, tr, axis, B, tgl=None):
         T, nb, D, H = ws['T'], self.num_bands, self.dim, self.heads
         M = ws['M']
@@ -412,8 +427,8 @@ class _RoformerBase(KernelModule):
             if self._tc:
                 t = tgl[si]
                 inner = self.inner
-                # RMSNorm (unit-norm rows; gamma*sqrt(D) lives in the weights) -> bf16 planes, + gate logits
-                tc.prep_rows(ws['x'], M, D, D, ws['xp'], True, s['gate_w'], s['gate_b'], ws['gates'], 8)
+                # xp holds the raw residual stream as bf16 planes and ss its row sums of squares (both written by the
+                # previous residual epilogue): RMSNorm is the consumer's row scale, gamma*sqrt(D) lives in the weights
                 t['qkv'].run(_epilogue(rot=rot, rot_cols=2 * inner, rot_dim=self.dim_head, pos_div=pos_div,
                                        pos_mod=pos_mod), nsplit)
                 qp, ap = ws['qkvp'], ws['aop']
@@ -421,7 +436,6 @@ class _RoformerBase(KernelModule):
                      ap.shape[-1], ap.stride(0), H, self.dim_head, n_seq, seq_len, inner_cnt, outer, inner_s, pos_s,
                      T if axis == 1 else 0, nsplit, 2, _stream())
                 t['out'].run(_epilogue(residual=1), nsplit)
-                tc.prep_rows(ws['x'], M, D, D, ws['xp'], True)
                 t['ff1'].run(_epilogue(act=_lib.ACT_GELU), nsplit)
                 t['ff2'].run(_epilogue(residual=1), nsplit)
                 continue
@@ -434,6 +448,8 @@ class _RoformerBase(KernelModule):
             self._gemm(g['ff2'], _epilogue(residual=1))
         if tr['norm'] is not None:
             call('sesa_rmsnorm', _ptr(ws['x']), _ptr(tr['norm']), _ptr(ws['x']), M, D, _stream())
+            if self._tc:
+                self._refresh_planes(ws)
 
     def forward(self, raw_audio, target=None, return_loss_breakdown=False, out=None):
         if target is not None:
@@ -455,10 +471,14 @@ class _RoformerBase(KernelModule):
              self.n_fft, self.hop, 0, F, st)
         self._gather_features(ws, prep, B, T)
         self._gemm(ws['g_bandsplit'], _epilogue(rownorm=1))
+        if self._tc:
+            self._refresh_planes(ws)
         for i, (pair, gp) in enumerate(zip(prep['layers'], ws['g_layers'])):
             if self.skip_connection:
                 for j in range(i):
                     call('sesa_add_inplace', _ptr(ws['x']), _ptr(ws['store'][j]), ws['x'].numel(), st)
+                if self._tc and i > 0:
+                    self._refresh_planes(ws)
             tgp = ws['t_layers'][i] if self._tc else (None, None)
             self._transformer(ws, prep, gp[0], pair[0], 0, B, tgp[0])
             self._transformer(ws, prep, gp[1], pair[1], 1, B, tgp[1])

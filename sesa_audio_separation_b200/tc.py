@@ -40,15 +40,17 @@ def split_weight(w):
 
 
 def prep_rows(x, rows, dim, ldx, planes, normalize, gate_w=None, gate_b=None, gates=None, ldg=0, rowinv=None,
-              out_planes=2):
-    """x fp32 [rows, ldx] -> bf16 planes (+ gate logits, + inverse row norms)."""
+              out_planes=2, ss_slots=1):
+    """x fp32 [rows, ldx] -> bf16 planes (+ gate logits, + inverse row norms).  normalize: False/0 raw, True/1 unit-norm
+    rows, 2 = raw planes and rowinv[rows, ss_slots] = (sum of squares, 0, ...) for a GEMM's fused row scale."""
     n_gates = 0 if gate_w is None else int(gate_w.shape[0])
-    call('sesa_prep_rows', _ptr(x), ldx, rows, dim, 1 if normalize else 0,
+    call('sesa_prep_rows', _ptr(x), ldx, rows, dim, int(normalize),
          _ptr(planes) if planes is not None else None,
          planes.shape[-1] if planes is not None else 0,
          planes.stride(0) if planes is not None else 0, out_planes,
          _ptr(gate_w) if gate_w is not None else None, _ptr(gate_b) if gate_b is not None else None, n_gates,
-         _ptr(gates) if gates is not None else None, ldg, _ptr(rowinv) if rowinv is not None else None, _stream())
+         _ptr(gates) if gates is not None else None, ldg, _ptr(rowinv) if rowinv is not None else None, ss_slots,
+         _stream())
 
 
 class TcGemmTable:
@@ -79,6 +81,9 @@ class TcGemmTable:
                     rec['conv_' + name] = conv[name]
                 rec['conv_dt'][:len(taps)] = [t[0] for t in taps]
                 rec['conv_df'][:len(taps)] = [t[1] for t in taps]
+            for name in ('rowss', 'ss_out', 'ss_slots', 'p_cols', 'c_col0'):
+                if p.get(name):
+                    rec[name] = p[name]
             rm = p.get('row_map')
             if rm is not None:        # (F_in, dt, df): 2x up-sampling scatter
                 rec['row_map'], rec['rm_F'], rec['rm_dt'], rec['rm_df'] = 1, rm[0], rm[1], rm[2]

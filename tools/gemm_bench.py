@@ -32,6 +32,12 @@ def main():
     qkv = torch.zeros(M, 1544, device=dev)
     w = {k: tc.split_weight(torch.randn(n, kk, device=dev, generator=g) / kk ** 0.5)
          for k, (n, kk) in dict(qkv=(1536, 512), out=(512, 512), ff1=(2048, 512), ff2=(512, 2048)).items()}
+    w['qkvg'] = tc.split_weight(torch.randn(1544, 512, device=dev, generator=g) / 512 ** 0.5)
+    gates = torch.zeros(M, 8, device=dev)
+    qkvp = tc.alloc_planes(M, 1536, dev)
+    xp2 = tc.alloc_planes(M, D, dev)
+    ss = torch.ones(M, 4, device=dev)
+    bg = torch.zeros(1544, device=dev)
     b1 = torch.randn(2048, device=dev, generator=g)
     b2 = torch.randn(512, device=dev, generator=g)
     ang = torch.einsum('i,j->ij', torch.arange(801, dtype=torch.float32), 1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64)))
@@ -47,6 +53,15 @@ def main():
                 GemmEpilogue(0, 1, 0, 0, 0, 0, 1, 1, None), 2 * M * 2048 * 512),
         'ff2': (table(hp, w['ff2'], 512, 2048, bias=b2.data_ptr(), C=(x.data_ptr(), 512)),
                 GemmEpilogue(0, 0, 1, 0, 0, 0, 1, 1, None), 2 * M * 512 * 2048),
+        'qkvg': (table(xp, w['qkvg'], 1544, 512, C=(gates.data_ptr(), 8), P=tc.planes_arg(qkvp), bias=bg.data_ptr(),
+                       rowss=ss.data_ptr(), ss_slots=4, p_cols=1536, c_col0=1536),
+                 GemmEpilogue(0, 0, 0, 0, 1024, 64, 62, 801, rot.data_ptr()), 2 * M * 1544 * 512),
+        'qkvp': (table(xp, w['qkv'], 1536, 512, P=tc.planes_arg(qkvp), rowss=ss.data_ptr(), ss_slots=4),
+                 GemmEpilogue(0, 0, 0, 0, 1024, 64, 62, 801, rot.data_ptr()), 2 * M * 1536 * 512),
+        'outp': (table(xp, w['out'], 512, 512, C=(x.data_ptr(), 512), P=tc.planes_arg(xp2), ss_out=ss.data_ptr()),
+                 GemmEpilogue(0, 0, 1, 0, 0, 0, 1, 1, None), 2 * M * 512 * 512),
+        'ff2p': (table(hp, w['ff2'], 512, 2048, bias=b2.data_ptr(), C=(x.data_ptr(), 512), P=tc.planes_arg(xp2), ss_out=ss.data_ptr()),
+                 GemmEpilogue(0, 0, 1, 0, 0, 0, 1, 1, None), 2 * M * 512 * 2048),
         'plain': (table(xp, w['ff1'], 2048, 512, C=(hp.data_ptr(), 2048)), GemmEpilogue(0, 0, 0, 0, 0, 0, 1, 1, None), 2 * M * 2048 * 512),
     }
     for name, (tab, ep, flops) in cases.items():
