@@ -1,5 +1,6 @@
 """GPU: model forward and demix parity against the committed golden vectors (produced by the
 unmodified reference) and against the CPU oracle, all through the C-ABI."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -166,3 +167,42 @@ def test_forward_is_batch_invariant(name):
     for i in range(x.shape[0]):
         yi = model(x[i:i + 1])
         assert torch.equal(yi[0], y[i]), (name, i, float((yi[0] - y[i]).abs().max()))
+
+
+def test_cli_inference_end_to_end(tmp_path, capsys):
+    """python -m sesa_audio_separation_b200.inference on a folder: the reference CLI flow (inference_pytorch.py:189-386)
+    with its output naming, --extract_instrumental and the [SESA_PROGRESS] protocol."""
+    import yaml
+    import sesa_audio_separation_b200 as sesa
+    from sesa_audio_separation_b200.audio_io import load_audio, write_audio
+    from sesa_audio_separation_b200.inference import proc_folder
+    case = CASES['bs_small']
+    mcfg = dict(case['cfg'])
+    mcfg['freqs_per_bands'] = tuple(mcfg['freqs_per_bands'])
+    L = 441 * 40
+    cfg = dict(audio=dict(chunk_size=L, sample_rate=44100, num_channels=2), model=mcfg,
+               training=dict(instruments=['vocals', 'other'], target_instrument='vocals', use_amp=False),
+               inference=dict(batch_size=1, num_overlap=2))
+    cfg_path = tmp_path / 'cfg.yaml'
+    cfg_path.write_text(yaml.dump(cfg))
+    model, config = sesa.get_model_from_config('bs_roformer', str(cfg_path))
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=31)
+    ckpt = tmp_path / 'model.ckpt'
+    torch.save({'state_dict': sd}, str(ckpt))
+    indir, outdir = tmp_path / 'in', tmp_path / 'out'
+    indir.mkdir()
+    mix = synth_mix(L * 3 + 500, 2, seed=32)
+    write_audio(str(indir / 'song.wav'), mix.T, 44100, subtype='FLOAT')
+    written = proc_folder(['--model_type', 'bs_roformer', '--config_path', str(cfg_path), '--start_check_point', str(ckpt),
+                           '--input_folder', str(indir), '--store_dir', str(outdir), '--extract_instrumental',
+                           '--export_format', 'wav FLOAT'])
+    names = sorted(os.path.basename(w) for w in written)
+    assert names == ['song.wav_instrumental.wav', 'song.wav_vocals.wav']
+    out = capsys.readouterr().out
+    assert '[SESA_PROGRESS]100' in out
+    model.load_state_dict(sd)
+    ref = sesa.demix(config, model.eval().to('cuda'), mix, 'cuda', 'bs_roformer')['vocals']
+    voc, _ = load_audio(str(outdir / 'song.wav_vocals.wav'), 44100)
+    ins, _ = load_audio(str(outdir / 'song.wav_instrumental.wav'), 44100)
+    assert np.array_equal(voc, ref)
+    assert np.allclose(ins, mix - ref, atol=1e-7)

@@ -121,3 +121,51 @@ def test_benchmark_yaml_configs_load_and_build():
         assert list(sesa.prefer_target_instrument(cfg)) == inst
     with pytest.raises(ValueError):
         sesa.get_model_from_config('scnet', os.path.join(ROOT, 'configs', 'config_vocals_mdx23c.yaml'))
+
+
+def test_audio_io_roundtrip_and_ensemble(tmp_path):
+    """CLI support code on the host: WAV writer/reader (FLOAT, PCM_16, PCM_24), resampling entry, waveform ensemble modes
+    against the reference's numpy statements (ensemble.py:172-183)."""
+    from sesa_audio_separation_b200.audio_io import load_audio, write_audio
+    from sesa_audio_separation_b200.ensemble import ensemble_waveforms, main as ens_main
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((2, 5000)) * 0.2).astype(np.float32)
+    for subtype, tol in (('FLOAT', 0.0), ('PCM_16', 2.0 ** -15), ('PCM_24', 2.0 ** -23)):
+        p = str(tmp_path / f'a_{subtype}.wav')
+        write_audio(p, x.T, 44100, subtype=subtype)
+        y, sr = load_audio(p, 44100)
+        assert sr == 44100 and y.shape == x.shape and np.abs(y - x).max() <= tol
+    y2, _ = load_audio(str(tmp_path / 'a_FLOAT.wav'), 22050)
+    assert y2.shape == (2, 2500)
+    stems = [x, x * 0.5 + 0.01, -x]
+    assert np.allclose(ensemble_waveforms(stems, 'avg_wave'), np.mean(stems, axis=0))
+    assert np.allclose(ensemble_waveforms(stems, 'avg_wave', [1, 2, 3]), np.average(stems, axis=0, weights=[1, 2, 3]))
+    assert np.array_equal(ensemble_waveforms(stems, 'median_wave'), np.median(stems, axis=0))
+    assert np.array_equal(ensemble_waveforms(stems, 'max_wave'), np.max(stems, axis=0))
+    t = [torch.from_numpy(s) for s in stems + [x * 2]]
+    assert np.allclose(ensemble_waveforms(t, 'median_wave').numpy(), np.median([s.numpy() for s in t], axis=0))
+    assert np.allclose(ensemble_waveforms(t, 'avg_wave', [1, 1, 2, 4]).numpy(), np.average([s.numpy() for s in t], axis=0, weights=[1, 1, 2, 4]), atol=1e-7)
+    files = []
+    for i, s in enumerate(stems):
+        f = str(tmp_path / f's{i}.wav')
+        write_audio(f, s.T, 44100, subtype='FLOAT')
+        files.append(f)
+    out = str(tmp_path / 'ens.wav')
+    with pytest.raises(SystemExit) as e:
+        ens_main(['--files', *files, '--type', 'avg_wave', '--output', out])
+    assert e.value.code == 0
+    got, _ = load_audio(out, 44100)
+    assert np.abs(got - np.mean(stems, axis=0)).max() < 2.0 ** -22
+    with pytest.raises(SystemExit) as e:
+        ens_main(['--files', *files, '--type', 'max_fft', '--output', out])
+    assert e.value.code == 1
+
+
+def test_cli_parser_accepts_reference_flags():
+    from sesa_audio_separation_b200.inference import build_parser, shorten_filename
+    a = build_parser().parse_args(['--model_type', 'bs_roformer', '--config_path', 'c.yaml', '--input_folder', 'in', '--store_dir',
+                                   'out', '--device_ids', '0', '--extract_instrumental', '--export_format', 'wav FLOAT',
+                                   '--pcm_type', 'PCM_16', '--use_tta', '--chunk_size', '485100', '--overlap', '2',
+                                   '--optimize_mode', 'channels_last', '--enable_amp', '--disable_detailed_pbar'])
+    assert a.model_type == 'bs_roformer' and a.device_ids == [0] and a.use_tta and a.enable_amp
+    assert shorten_filename('a' * 40 + '.wav') == 'a' * 15 + '...' + 'a' * 10 + '.wav'
