@@ -178,7 +178,8 @@ def test_cli_inference_end_to_end(tmp_path, capsys):
     from sesa_audio_separation_b200.inference import proc_folder
     case = CASES['bs_small']
     mcfg = dict(case['cfg'])
-    mcfg['freqs_per_bands'] = tuple(mcfg['freqs_per_bands'])
+    if 'freqs_per_bands' in mcfg:
+        mcfg['freqs_per_bands'] = tuple(mcfg['freqs_per_bands'])
     L = 441 * 40
     cfg = dict(audio=dict(chunk_size=L, sample_rate=44100, num_channels=2), model=mcfg,
                training=dict(instruments=['vocals', 'other'], target_instrument='vocals', use_amp=False),
