@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SESA_B200_ABI_VERSION 1
+#define SESA_B200_ABI_VERSION 2
 
 enum { SESA_ACT_NONE = 0, SESA_ACT_GELU = 1, SESA_ACT_TANH = 2, SESA_ACT_SIGMOID = 3 };
 
@@ -140,13 +140,15 @@ int64_t sesa_gemm_tc_table_bytes(int n_groups);
 /* Encode the TMA tensor maps and tile ranges of n_groups problems into table_host (host memory of
  * sesa_gemm_tc_table_bytes(n_groups) bytes); the caller copies the table to the device and keeps it while
  * the pointers stay valid.  *total_tiles receives the number of 128 x block_n output tiles. */
-int sesa_gemm_tc_build(const sesa_tc_problem* problems_host, int n_groups, int block_n, void* table_host,
+int sesa_gemm_tc_build(const sesa_tc_problem* problems_host, int n_groups, int block_n, int cta_group, void* table_host,
                        int* total_tiles);
 /* Grouped GEMM on the 5th-gen tensor cores (nn.Linear call sites bs_roformer.py:63,67,99,104,237,264):
  * TMA-fed, tcgen05.mma into TMEM, persistent over tiles.  Epilogue fields of sesa_gemm_epilogue apply except
- * `rownorm` (use sesa_tc_problem.rowscale).  block_n in {128, 256}; nsplit in {1, 3}; out_planes in {1, 2}. */
-int sesa_gemm_tc(const void* table_dev, int n_groups, int total_tiles, int block_n, int nsplit, int out_planes,
-                 const sesa_gemm_epilogue* ep_host, void* stream);
+ * `rownorm` (use sesa_tc_problem.rowscale).  block_n in {128, 256}; nsplit in {1, 3}; out_planes in {1, 2};
+ * cta_group 1 = one CTA per 128 x block_n tile, 2 = a CTA pair (thread-block cluster of 2, tcgen05 cta_group::2) per
+ * 256 x 256 tile, each CTA staging half of the W tile (must match the value given to sesa_gemm_tc_build). */
+int sesa_gemm_tc(const void* table_dev, int n_groups, int total_tiles, int block_n, int cta_group, int nsplit,
+                 int out_planes, const sesa_gemm_epilogue* ep_host, void* stream);
 /* Tensor-core attention (attend.py:89-93; gating and head merge bs_roformer.py:115-120).  qkv_planes: bf16
  * [planes][rows][ld] with row layout [q(h d) | k(h d) | v(h d)] (q pre-scaled, q/k rotated); gates: fp32 logits
  * [rows][ldg]; out_planes: bf16 [out_planes][rows][ldo] = softmax(q k^T) v * sigmoid(gate), heads merged.

@@ -59,8 +59,8 @@ _SIGS = {
     'sesa_attention_simt': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int64, c_int64, c_int64, c_void_p]),
     'sesa_gemm_tc_table_bytes': (c_int64, [c_int]),
-    'sesa_gemm_tc_build': (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_int)]),
-    'sesa_gemm_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(GemmEpilogue), c_void_p]),
+    'sesa_gemm_tc_build': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, POINTER(c_int)]),
+    'sesa_gemm_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(GemmEpilogue), c_void_p]),
     'sesa_attention_tc': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int,
                                   c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     'sesa_prep_rows': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_int64, c_int,
@@ -103,7 +103,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.sesa_abi_version() != 1:
+    if lib.sesa_abi_version() != 2:
         raise SesaError('libsesa_b200.so ABI version mismatch')
     _lib = lib
     return lib

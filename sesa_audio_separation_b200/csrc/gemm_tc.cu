@@ -52,11 +52,11 @@ struct alignas(128) TcGroup {
 };
 static_assert(sizeof(TcGroup) % 128 == 0, "table entries must keep the tensor maps 128-byte aligned");
 
-template <int BN, int NSPLIT>
+template <int BN, int NSPLIT, int CG = 1>
 struct Cfg {
   static constexpr int NP = NSPLIT == 3 ? 2 : 1;           // planes staged per operand
   static constexpr int A_BYTES = BM * BK * 2;               // 16 KB per plane
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;        // a CTA pair (CG = 2) splits the W tile's rows
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (196 * 1024) / STAGE_BYTES >= 6 ? 6 : (196 * 1024) / STAGE_BYTES;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
@@ -115,11 +115,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // instruction cache (one epilogue warp per scheduler cannot hide instruction-fetch misses).
 enum { F_PLAIN = 0, F_ROT = 1, F_GELU = 2, F_TANH = 3, F_GLU = 4, F_GENERIC = 5 };
 
-template <int BN, int NSPLIT, int FLAVOR>
+// CG = 2: two CTAs of a cluster (one TPC) work on one 256 x BN tile with cta_group::2 MMAs: each CTA stages its own 128
+// rows of A and HALF of the W tile, the leader CTA issues one M = 256 MMA over both shared memories, and each CTA's
+// TMEM receives its 128 accumulator rows.  That halves the W traffic from L2 and through shared memory.
+template <int BN, int NSPLIT, int FLAVOR, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles, sesa_gemm_epilogue ep,
                int out_planes) {
-  using C = Cfg<BN, NSPLIT>;
+  using C = Cfg<BN, NSPLIT, CG>;
+  const int cta_rank = CG == 2 ? (int)tc::cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CG;         // CTA (pair) index: the tile scheduler's granularity
+  const int n_units = gridDim.x / CG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -142,16 +149,21 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(&tmem_full[a], 1);
-      tc::mbar_init(&tmem_empty[a], EPI_WARPS);
+      tc::mbar_init(&tmem_empty[a], EPI_WARPS * CG);   // the leader's copy collects both CTAs' epilogue warps
     }
     tc::fence_barrier_init();
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_ptr, C::TMEM_COLS);
-    tc::tmem_relinquish();
+    if (CG == 2) {
+      tc::tmem_alloc_2sm(tmem_ptr, C::TMEM_COLS);
+      tc::tmem_relinquish_2sm();
+    } else {
+      tc::tmem_alloc(tmem_ptr, C::TMEM_COLS);
+      tc::tmem_relinquish();
+    }
   }
   tc::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) tc::cluster_sync(); else __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -160,12 +172,17 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     if (tc::elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
         const int t = tile - g->tile_begin;
-        const int mb = t / g->n_blocks, nb = t % g->n_blocks;
+        const int mb = (t / g->n_blocks) * CG + cta_rank, nb = t % g->n_blocks;
         const int kbs = g->k_blocks;
         const int taps = g->taps;
+        // a pair splits the columns the MMA really multiplies (see n_eff in the issuer): CTA r stages W rows
+        // [r * n_eff / 2, (r + 1) * n_eff / 2) of the tile
+        const int n_left_p = g->N - nb * BN;
+        const int n_eff_p = n_left_p >= BN ? BN : ((n_left_p + 16 * CG - 1) & ~(16 * CG - 1));
+        const int w_row0 = nb * BN + cta_rank * (n_eff_p / 2);
         int cf0 = 0, ct0 = 0, cb = 0, kbpt = 1;
         if (taps > 0) {   // output pixel (b, t0, f0) of the tile's first row
           const int m0 = mb * BM;
@@ -177,7 +194,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
         }
         for (int kb = 0; kb < kbs; ++kb) {
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
-          tc::mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          if (leader) tc::mbar_expect_tx(&full_bar[s], C::STAGE_BYTES * CG);   // bytes of both CTAs land on the leader's barrier
           uint8_t* sa = stage_base + s * C::STAGE_BYTES;
           uint8_t* sb = sa + C::NP * C::A_BYTES;
           if (taps > 0) {
@@ -186,32 +203,40 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             const int tap = kb / kbpt;
             const int c0 = (kb - tap * kbpt) * BK;
 #pragma unroll
-            for (int p = 0; p < C::NP; ++p)
-              tc::tma_load_5d(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], c0, cf0 + g->tap_df[tap], ct0 + g->tap_dt[tap], cb, p);
+            for (int p = 0; p < C::NP; ++p) {
+              if (CG == 2) tc::tma_load_5d_2sm(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], c0, cf0 + g->tap_df[tap], ct0 + g->tap_dt[tap], cb, p);
+              else tc::tma_load_5d(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], c0, cf0 + g->tap_df[tap], ct0 + g->tap_dt[tap], cb, p);
+            }
           } else {
 #pragma unroll
-            for (int p = 0; p < C::NP; ++p) tc::tma_load_3d(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], kb * BK, mb * BM, p);
+            for (int p = 0; p < C::NP; ++p) {
+              if (CG == 2) tc::tma_load_3d_2sm(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], kb * BK, mb * BM, p);
+              else tc::tma_load_3d(sa + p * C::A_BYTES, &g->mapA, &full_bar[s], kb * BK, mb * BM, p);
+            }
           }
 #pragma unroll
-          for (int p = 0; p < C::NP; ++p) tc::tma_load_3d(sb + p * C::B_BYTES, &g->mapW, &full_bar[s], kb * BK, nb * BN, p);
+          for (int p = 0; p < C::NP; ++p) {
+            if (CG == 2) tc::tma_load_3d_2sm(sb + p * C::B_BYTES, &g->mapW, &full_bar[s], kb * BK, w_row0, p);
+            else tc::tma_load_3d(sb + p * C::B_BYTES, &g->mapW, &full_bar[s], kb * BK, nb * BN, p);
+          }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (tc::elect_one()) {
+    if (leader && tc::elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
         const int kbs = g->k_blocks;
-        // the last column block of a problem only multiplies the columns that exist (N granularity 16)
+        // the last column block of a problem only multiplies the columns that exist (N granularity 16; 32 for a pair)
         const int n_left = g->N - ((tile - g->tile_begin) % g->n_blocks) * BN;
-        const int n_eff = n_left >= BN ? BN : ((n_left + 15) & ~15);
-        const uint32_t idesc = tc::make_idesc_bf16(BM, n_eff, 0, 0);
+        const int n_eff = n_left >= BN ? BN : ((n_left + 16 * CG - 1) & ~(16 * CG - 1));
+        const uint32_t idesc = tc::make_idesc_bf16(BM * CG, n_eff, 0, 0);
         tc::mbar_wait(&tmem_empty[as], aph ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -229,79 +254,84 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t ad = tc::make_smem_desc_sw128(a_addr + k * UMMA_K * 2);
               const uint64_t bd = tc::make_smem_desc_sw128(b_addr + k * UMMA_K * 2);
-              tc::umma_f16(d_tmem, ad, bd, idesc, (kb | prod | k) != 0 ? 1u : 0u);
+              if (CG == 2) tc::umma_f16_2sm(d_tmem, ad, bd, idesc, (kb | prod | k) != 0 ? 1u : 0u);
+              else tc::umma_f16(d_tmem, ad, bd, idesc, (kb | prod | k) != 0 ? 1u : 0u);
             }
           }
-          tc::umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if (CG == 2) tc::umma_commit_2sm(&empty_bar[s], 3); else tc::umma_commit(&empty_bar[s]);
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
-        tc::umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CG == 2) tc::umma_commit_2sm(&tmem_full[as], 3); else tc::umma_commit(&tmem_full[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
   } else {
     // ================= epilogue warps =================
-    // Phase A (thread = accumulator row): TMEM -> registers, scale / bias / activation / rotary.
-    // Phase B (after a conflict-free transpose through shared memory): 4 lanes cover one row's 16 columns, so
-    // the residual read, the fp32 store and the bf16 plane stores are all sector-complete and coalesced.
+    // Phase A (thread = accumulator row): TMEM -> registers -> XOR-swizzled shared memory (raw accumulators).
+    // Phase B (4 lanes per row, 4 columns per lane): row scale, bias, activation, rotary, GLU, residual, row sum of
+    // squares, and the fp32 / bf16-plane stores — every global access is sector-complete and coalesced, and the
+    // per-element arithmetic works on float4s with per-lane constants (bias quad, rotary quad).
     const int ew = warp - 2;
     const int q = warp & 3;          // TMEM lane quadrant this warp may access
     const int ch = ew >> 2;          // which half of the tile's columns
     constexpr int HALF = BN / 2;
     const uint32_t stage = tc::smem_u32(smem + C::EPI_OFF + ew * EPI_STAGE_BYTES);   // byte address in shared space
+    constexpr bool kGeneric = FLAVOR == F_GENERIC;
+    const bool use_glu = FLAVOR == F_GLU || (kGeneric && ep.glu);
+    const int act = FLAVOR == F_GELU ? SESA_ACT_GELU : FLAVOR == F_TANH ? SESA_ACT_TANH : kGeneric ? ep.act : SESA_ACT_NONE;
+    const int rot_cols = (FLAVOR == F_ROT || kGeneric) ? ep.rot_cols : 0;
+    const int c4 = lane & 3;         // phase B: this lane's column quad inside a 16-column step
+    const int rb = lane >> 2;        // phase B: row (within each group of 8) handled by this lane
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < total_tiles; tile += n_units) {
       const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
       const int t = tile - g->tile_begin;
-      const int mb = t / g->n_blocks, nb = t % g->n_blocks;
+      const int mb = (t / g->n_blocks) * CG + cta_rank, nb = t % g->n_blocks;
       const int M = g->M, N = g->N;
       const int m_base = mb * BM + q * 32;
-      const int m = m_base + lane;
-      const bool row_ok = m < M;
       const int n_half = nb * BN + ch * HALF;
       const float* __restrict__ bias = g->bias;
       float* __restrict__ Cp = g->C;
       __nv_bfloat16* __restrict__ Pp = g->P;
       const int64_t ldc = g->ldc, ldp = g->ldp, p_plane = g->p_plane;
-      float rs = (g->rowscale != nullptr && row_ok) ? g->rowscale[m] : 1.0f;
-      if (g->rowss != nullptr && row_ok) {   // fused RMSNorm: F.normalize(x, dim=-1) of the GEMM input (bs_roformer.py:49)
-        float ssum = 0.f;
-        for (int k = 0; k < g->ss_slots; ++k) ssum += g->rowss[(int64_t)m * g->ss_slots + k];
-        rs = 1.0f / fmaxf(sqrtf(ssum), 1e-12f);
-      }
       float* __restrict__ ss_out = g->ss_out;
-      const int p_cols = g->p_cols > 0 ? g->p_cols : N;
+      const int p_cols = g->p_cols > 0 ? g->p_cols : (use_glu ? N >> 1 : N);
       const int c_col0 = g->c_col0;
-      float ssq[4] = {0.f, 0.f, 0.f, 0.f};
-      int pos = 0;
-      if ((FLAVOR == F_ROT || FLAVOR == F_GENERIC) && ep.rot_cols > 0) pos = (m / ep.pos_div) % ep.pos_mod;
       const int row_map = g->row_map, rm_F = g->rm_F, rm_dt = g->rm_dt, rm_df = g->rm_df;
-      auto out_row = [&](int mm) -> int64_t {
-        if (row_map == 0) return mm;
-        const int q = mm / rm_F;
-        return (int64_t)(2 * q + rm_dt) * (2 * rm_F) + 2 * (mm - q * rm_F) + rm_df;
-      };
-      const bool c_vec = Cp == nullptr || ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
-      const bool p_vec = Pp == nullptr || ((ldp & 3) == 0 && (p_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(Pp) & 7) == 0);
-      constexpr bool kGeneric = FLAVOR == F_GENERIC;
-      const bool use_glu = FLAVOR == F_GLU || (kGeneric && ep.glu);
-      const int act = FLAVOR == F_GELU ? SESA_ACT_GELU : FLAVOR == F_TANH ? SESA_ACT_TANH : kGeneric ? ep.act : SESA_ACT_NONE;
-      const int rot_cols = (FLAVOR == F_ROT || kGeneric) ? ep.rot_cols : 0;
-      const bool staged = c_vec && p_vec && !use_glu;
-      // this lane's slice of the bias for the warp's column half (columns n_half + 4*lane ..)
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias != nullptr && lane * 4 < HALF) {
-        const int bc = n_half + lane * 4;
-        if (bc + 3 < N && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
-          b4 = __ldg(reinterpret_cast<const float4*>(bias + bc));
-        } else {
-          if (bc < N) b4.x = bias[bc];
-          if (bc + 1 < N) b4.y = bias[bc + 1];
-          if (bc + 2 < N) b4.z = bias[bc + 2];
-          if (bc + 3 < N) b4.w = bias[bc + 3];
+      // per-lane constants of the 4 rows this lane finishes in phase B (rows it*8 + rb of the warp's 32)
+      float rs4[4];
+      int64_t orow4[4];
+      int pos4[4];
+      bool ok4[4];
+      float ssq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int mm = m_base + it * 8 + rb;
+        ok4[it] = mm < M;
+        float r = 1.0f;
+        if (ok4[it]) {
+          if (g->rowscale != nullptr) r = g->rowscale[mm];
+          if (g->rowss != nullptr) {   // fused RMSNorm: F.normalize(x, dim=-1) of the GEMM input (bs_roformer.py:49)
+            float ssum = 0.f;
+            for (int k = 0; k < g->ss_slots; ++k) ssum += g->rowss[(int64_t)mm * g->ss_slots + k];
+            r = 1.0f / fmaxf(sqrtf(ssum), 1e-12f);
+          }
         }
+        rs4[it] = r;
+        if (row_map == 0) orow4[it] = mm;
+        else {
+          const int qq = mm / rm_F;
+          orow4[it] = (int64_t)(2 * qq + rm_dt) * (2 * rm_F) + 2 * (mm - qq * rm_F) + rm_df;
+        }
+        pos4[it] = rot_cols > 0 ? (mm / ep.pos_div) % ep.pos_mod : 0;
       }
+      const bool c_vec = Cp == nullptr || ((ldc & 3) == 0 && (c_col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
+      const bool p_vec = Pp == nullptr || ((ldp & 3) == 0 && (p_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(Pp) & 7) == 0);
+      const bool b_vec = bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+      const bool vec_ok = c_vec && p_vec && b_vec;
 
       tc::mbar_wait(&tmem_full[as], aph);
       tc::tc_fence_after();
@@ -310,142 +340,183 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       for (int c = 0; c < HALF / EPI_COLS; ++c) {
         const int n = n_half + c * EPI_COLS;
         if (n >= N) break;  // warp-uniform
-        // phase-B coordinates of this lane: rows it*8 + lane/4, columns n + 4*(lane%4) ..
-        const int c4 = lane & 3;
         const int colb = n + c4 * 4;
-        float4 res[4];
-        if (staged && ep.residual) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int mm = m_base + it * 8 + (lane >> 2);
-            res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (mm < M && colb + 3 < N) res[it] = *reinterpret_cast<const float4*>(Cp + out_row(mm) * ldc + colb);
-          }
-        }
-        float4 rt4[4];
-        const bool do_rot = n < rot_cols;
-        if (do_rot) {
-          const float4* rp = reinterpret_cast<const float4*>(ep.rot) +
-                             (((int64_t)pos * (ep.rot_dim >> 1) + ((n % ep.rot_dim) >> 1)) >> 1);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) rt4[i] = __ldg(rp + i);
-        }
-        float v[EPI_COLS];
-        tmem_ld16(t_row + c * EPI_COLS, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < EPI_COLS; ++j) {
-          const int src = c * 4 + (j >> 2);
-          const float bsel = (j & 3) == 0 ? b4.x : (j & 3) == 1 ? b4.y : (j & 3) == 2 ? b4.z : b4.w;
-          v[j] = fmaf(v[j], rs, __shfl_sync(0xffffffffu, bsel, src));
-        }
-        if (act == SESA_ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < EPI_COLS; ++j) v[j] = gelu_fast(v[j]);
-        } else if (act == SESA_ACT_TANH) {
-#pragma unroll
-          for (int j = 0; j < EPI_COLS; ++j) v[j] = tanhf(v[j]);
-        } else if (act == SESA_ACT_SIGMOID) {
-#pragma unroll
-          for (int j = 0; j < EPI_COLS; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
-        }
-        if (do_rot) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float x1 = v[4 * i], x2 = v[4 * i + 1], x3 = v[4 * i + 2], x4 = v[4 * i + 3];
-            v[4 * i] = x1 * rt4[i].x - x2 * rt4[i].y;
-            v[4 * i + 1] = x2 * rt4[i].x + x1 * rt4[i].y;
-            v[4 * i + 2] = x3 * rt4[i].z - x4 * rt4[i].w;
-            v[4 * i + 3] = x4 * rt4[i].z + x3 * rt4[i].w;
-          }
-        }
-        if (staged) {
-          // transpose through shared memory; 16-byte blocks XOR-swizzled by (row>>1)&3: both phases conflict-free
+        // ---- phase A
+        {
+          float v[EPI_COLS];
+          tmem_ld16(t_row + c * EPI_COLS, v);
+          tc::tmem_ld_wait();
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4)
             sts128(stage + lane * (EPI_COLS * 4) + ((j4 ^ ((lane >> 1) & 3)) << 4),
                    make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
-          __syncwarp();
+        }
+        // per-lane constants of this step: bias quad (same columns for all 4 rows)
+        const bool interior = vec_ok && n + EPI_COLS <= N;   // warp-uniform: no ragged right edge in this step
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias != nullptr) {
+          if (interior) b4 = __ldg(reinterpret_cast<const float4*>(bias + colb));
+          else {
+            if (colb < N) b4.x = bias[colb];
+            if (colb + 1 < N) b4.y = bias[colb + 1];
+            if (colb + 2 < N) b4.z = bias[colb + 2];
+            if (colb + 3 < N) b4.w = bias[colb + 3];
+          }
+        }
+        const bool do_rot = n < rot_cols;
+        const int rot_d = do_rot ? ((colb % ep.rot_dim) >> 1) : 0;   // first of the two (cos, sin) pairs of this quad
+        float4 res[4];
+        if (ep.residual && interior) {   // issue the residual reads before the shared-memory round trip completes
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            res[it] = ok4[it] ? *reinterpret_cast<const float4*>(Cp + orow4[it] * ldc + (colb - c_col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        // ---- phase B
+        if (interior && !use_glu) {
+          // fast path: straight-line code over the lane's 4 rows (16 independent element chains for the scheduler);
+          // only the stores are predicated
+          float4 o[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            const int r = it * 8 + (lane >> 2);
-            const int mm = m_base + r;
-            float4 o = lds128(stage + r * (EPI_COLS * 4) + ((c4 ^ ((r >> 1) & 3)) << 4));
-            if (mm >= M || colb >= N) continue;
-            const int64_t orow = out_row(mm);
-            if (colb + 3 < N) {
-              if (ep.residual) { o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w; }
-              ssq[it] += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
-              if (Cp != nullptr && colb >= c_col0) *reinterpret_cast<float4*>(Cp + orow * ldc + (colb - c_col0)) = o;
-              if (Pp != nullptr && colb < p_cols) {
-                __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-                tc::split_bf16(o.x, h0, l0); tc::split_bf16(o.y, h1, l1);
-                tc::split_bf16(o.z, h2, l2); tc::split_bf16(o.w, h3, l3);
-                __nv_bfloat16* pr = Pp + orow * ldp + colb;
-                *reinterpret_cast<uint2*>(pr) = make_uint2(tc::pack_bf16(h0, h1), tc::pack_bf16(h2, h3));
-                if (out_planes > 1) *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(tc::pack_bf16(l0, l1), tc::pack_bf16(l2, l3));
-              }
-            } else {  // ragged right edge of the problem
-              const float ov[4] = {o.x, o.y, o.z, o.w};
-              for (int e = 0; e < 4 && colb + e < N; ++e) {
-                float val = ov[e];
-                if (Cp != nullptr && colb + e >= c_col0) {
-                  float* cp = Cp + orow * ldc + colb + e - c_col0;
-                  if (ep.residual) val += *cp;
-                  *cp = val;
-                }
-                ssq[it] += val * val;
-                if (Pp != nullptr && colb + e < p_cols) {
-                  __nv_bfloat16 h, l;
-                  tc::split_bf16(val, h, l);
-                  Pp[orow * ldp + colb + e] = h;
-                  if (out_planes > 1) Pp[orow * ldp + p_plane + colb + e] = l;
-                }
+            const int r = it * 8 + rb;
+            o[it] = lds128(stage + r * (EPI_COLS * 4) + ((c4 ^ ((r >> 1) & 3)) << 4));
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            o[it].x = fmaf(o[it].x, rs4[it], b4.x);
+            o[it].y = fmaf(o[it].y, rs4[it], b4.y);
+            o[it].z = fmaf(o[it].z, rs4[it], b4.z);
+            o[it].w = fmaf(o[it].w, rs4[it], b4.w);
+          }
+          if (act == SESA_ACT_GELU) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              o[it].x = gelu_fast(o[it].x); o[it].y = gelu_fast(o[it].y);
+              o[it].z = gelu_fast(o[it].z); o[it].w = gelu_fast(o[it].w);
+            }
+          } else if (act == SESA_ACT_TANH) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              o[it].x = tanhf(o[it].x); o[it].y = tanhf(o[it].y); o[it].z = tanhf(o[it].z); o[it].w = tanhf(o[it].w);
+            }
+          } else if (act == SESA_ACT_SIGMOID) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              o[it].x = 1.0f / (1.0f + expf(-o[it].x)); o[it].y = 1.0f / (1.0f + expf(-o[it].y));
+              o[it].z = 1.0f / (1.0f + expf(-o[it].z)); o[it].w = 1.0f / (1.0f + expf(-o[it].w));
+            }
+          }
+          if (do_rot) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rot_d) >> 1));
+              const float x1 = o[it].x, x2 = o[it].y, x3 = o[it].z, x4 = o[it].w;
+              o[it].x = x1 * cs.x - x2 * cs.y;
+              o[it].y = x2 * cs.x + x1 * cs.y;
+              o[it].z = x3 * cs.z - x4 * cs.w;
+              o[it].w = x4 * cs.z + x3 * cs.w;
+            }
+          }
+          if (ep.residual) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) { o[it].x += res[it].x; o[it].y += res[it].y; o[it].z += res[it].z; o[it].w += res[it].w; }
+          }
+          const bool wc = Cp != nullptr && colb >= c_col0;
+          const bool wp = Pp != nullptr && colb < p_cols;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            ssq[it] += o[it].x * o[it].x + o[it].y * o[it].y + o[it].z * o[it].z + o[it].w * o[it].w;
+            if (wc && ok4[it]) *reinterpret_cast<float4*>(Cp + orow4[it] * ldc + (colb - c_col0)) = o[it];
+            if (wp) {
+              uint32_t h0, l0, h1, l1;
+              tc::split_bf16x2(o[it].x, o[it].y, h0, l0);
+              tc::split_bf16x2(o[it].z, o[it].w, h1, l1);
+              if (ok4[it]) {
+                __nv_bfloat16* pr = Pp + orow4[it] * ldp + colb;
+                *reinterpret_cast<uint2*>(pr) = make_uint2(h0, h1);
+                if (out_planes > 1) *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(l0, l1);
               }
             }
           }
-          __syncwarp();
-        } else if (row_ok) {
-          // generic path (GLU or unaligned outputs): each thread writes its own row
-          int width = EPI_COLS, nbase = n, nlimit = N;
-          if (use_glu) {  // rows of W interleaved (value, gate): out[:, n/2 + j] = v[2j] * sigmoid(v[2j+1])
+        } else {
 #pragma unroll
-            for (int j = 0; j < EPI_COLS / 2; ++j) v[j] = v[2 * j] * (1.0f / (1.0f + expf(-v[2 * j + 1])));
-            width = EPI_COLS / 2;
-            nbase = n >> 1;
-            nlimit = N >> 1;
-          }
-#pragma unroll
-          for (int j = 0; j < EPI_COLS; ++j) {
-            if (j < width && nbase + j < nlimit) {
-              float val = v[j];
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + rb;
+            float4 o = lds128(stage + r * (EPI_COLS * 4) + ((c4 ^ ((r >> 1) & 3)) << 4));
+            if (!ok4[it]) continue;
+            o.x = fmaf(o.x, rs4[it], b4.x);
+            o.y = fmaf(o.y, rs4[it], b4.y);
+            o.z = fmaf(o.z, rs4[it], b4.z);
+            o.w = fmaf(o.w, rs4[it], b4.w);
+            if (act == SESA_ACT_GELU) {
+              o.x = gelu_fast(o.x); o.y = gelu_fast(o.y); o.z = gelu_fast(o.z); o.w = gelu_fast(o.w);
+            } else if (act == SESA_ACT_TANH) {
+              o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
+            } else if (act == SESA_ACT_SIGMOID) {
+              o.x = 1.0f / (1.0f + expf(-o.x)); o.y = 1.0f / (1.0f + expf(-o.y));
+              o.z = 1.0f / (1.0f + expf(-o.z)); o.w = 1.0f / (1.0f + expf(-o.w));
+            }
+            if (do_rot) {
+              const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rot_d) >> 1));
+              const float x1 = o.x, x2 = o.y, x3 = o.z, x4 = o.w;
+              o.x = x1 * cs.x - x2 * cs.y;
+              o.y = x2 * cs.x + x1 * cs.y;
+              o.z = x3 * cs.z - x4 * cs.w;
+              o.w = x4 * cs.z + x3 * cs.w;
+            }
+            const int64_t orow = orow4[it];
+            if (use_glu) {
+              // W rows interleaved (value, gate): out[:, colb/2 + {0,1}] = (o.x * sigmoid(o.y), o.z * sigmoid(o.w))
+              const float g0 = o.x * (1.0f / (1.0f + expf(-o.y)));
+              const float g1 = o.z * (1.0f / (1.0f + expf(-o.w)));
+              const int oc = colb >> 1;
               if (Cp != nullptr) {
-                float* cp = Cp + out_row(m) * ldc + nbase + j;
-                if (ep.residual) val += *cp;
-                *cp = val;
+                float* cp = Cp + orow * ldc + oc;
+                if (colb + 1 < N) cp[0] = g0;
+                if (colb + 3 < N) cp[1] = g1;
               }
               if (Pp != nullptr) {
                 __nv_bfloat16 h, l;
+                if (colb + 1 < N) { tc::split_bf16(g0, h, l); Pp[orow * ldp + oc] = h; if (out_planes > 1) Pp[orow * ldp + p_plane + oc] = l; }
+                if (colb + 3 < N) { tc::split_bf16(g1, h, l); Pp[orow * ldp + oc + 1] = h; if (out_planes > 1) Pp[orow * ldp + p_plane + oc + 1] = l; }
+              }
+              continue;
+            }
+            // ragged right edge of the problem, or unaligned outputs
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+            for (int e = 0; e < 4 && colb + e < N; ++e) {
+              float val = ov[e];
+              if (Cp != nullptr && colb + e >= c_col0) {
+                float* cp = Cp + orow * ldc + colb + e - c_col0;
+                if (ep.residual) val += *cp;
+                *cp = val;
+              }
+              ssq[it] += val * val;
+              if (Pp != nullptr && colb + e < p_cols) {
+                __nv_bfloat16 h, l;
                 tc::split_bf16(val, h, l);
-                Pp[out_row(m) * ldp + nbase + j] = h;
-                if (out_planes > 1) Pp[out_row(m) * ldp + p_plane + nbase + j] = l;
+                Pp[orow * ldp + colb + e] = h;
+                if (out_planes > 1) Pp[orow * ldp + p_plane + colb + e] = l;
               }
             }
           }
         }
+        __syncwarp();
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tmem_empty[as]);
-      if (ss_out != nullptr) {   // this warp's slot of the row sums of squares (rows it*8 + lane/4, 4 lanes per row)
+      if (lane == 0) {
+        if (CG == 2) tc::mbar_arrive_leader(&tmem_empty[as]); else tc::mbar_arrive(&tmem_empty[as]);
+      }
+      if (ss_out != nullptr) {   // this warp's slot of the row sums of squares (4 lanes per row)
         const int slots = 2 * g->n_blocks;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float v = ssq[it];
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
-          const int mm = m_base + it * 8 + (lane >> 2);
-          if ((lane & 3) == 0 && mm < M) ss_out[out_row(mm) * slots + 2 * nb + ch] = v;
+          if (c4 == 0 && ok4[it]) ss_out[orow4[it] * slots + 2 * nb + ch] = v;
         }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
@@ -453,18 +524,20 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
   }
 
   tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (CG == 2) tc::cluster_sync(); else __syncthreads();
+  if (warp == 1) {
+    if (CG == 2) tc::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS); else tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
 }
 
-template <int BN, int NSPLIT, int FLAVOR>
+template <int BN, int NSPLIT, int FLAVOR, int CG>
 int launch_gemm_tc_f(const TcGroup* table, int n_groups, int total_tiles, const sesa_gemm_epilogue& ep, int out_planes,
                      cudaStream_t stream) {
-  using C = Cfg<BN, NSPLIT>;
+  using C = Cfg<BN, NSPLIT, CG>;
   static_assert(C::STAGES >= 2, "pipeline needs at least two stages");
   static bool configured = false;
   if (!configured) {
-    SESA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, NSPLIT, FLAVOR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SESA_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, NSPLIT, FLAVOR, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    C::SMEM_BYTES));
     configured = true;
   }
@@ -474,14 +547,25 @@ int launch_gemm_tc_f(const TcGroup* table, int n_groups, int total_tiles, const 
     SESA_CUDA(cudaGetDevice(&dev));
     SESA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = total_tiles < sms ? total_tiles : sms;
-  gemm_tc_kernel<BN, NSPLIT, FLAVOR><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(table, n_groups, total_tiles, ep,
-                                                                                   out_planes);
-  SESA_LAUNCH_CHECK();
+  const int units = sms / CG;   // persistent CTAs (CTA pairs): one per SM (TPC)
+  const int grid = (total_tiles < units ? total_tiles : units) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SESA_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NSPLIT, FLAVOR, CG>, table, n_groups, total_tiles, ep, out_planes));
   return SESA_OK;
 }
 
-template <int BN, int NSPLIT>
+template <int BN, int NSPLIT, int CG>
 int launch_gemm_tc(const TcGroup* table, int n_groups, int total_tiles, const sesa_gemm_epilogue& ep, int out_planes,
                    cudaStream_t stream) {
   int flavor = F_GENERIC;
@@ -491,12 +575,12 @@ int launch_gemm_tc(const TcGroup* table, int n_groups, int total_tiles, const se
   else if (!ep.glu && ep.rot_cols == 0 && ep.act == SESA_ACT_GELU) flavor = F_GELU;
   else if (!ep.glu && ep.rot_cols == 0 && ep.act == SESA_ACT_TANH) flavor = F_TANH;
   switch (flavor) {
-    case F_PLAIN: return launch_gemm_tc_f<BN, NSPLIT, F_PLAIN>(table, n_groups, total_tiles, ep, out_planes, stream);
-    case F_ROT: return launch_gemm_tc_f<BN, NSPLIT, F_ROT>(table, n_groups, total_tiles, ep, out_planes, stream);
-    case F_GELU: return launch_gemm_tc_f<BN, NSPLIT, F_GELU>(table, n_groups, total_tiles, ep, out_planes, stream);
-    case F_TANH: return launch_gemm_tc_f<BN, NSPLIT, F_TANH>(table, n_groups, total_tiles, ep, out_planes, stream);
-    case F_GLU: return launch_gemm_tc_f<BN, NSPLIT, F_GLU>(table, n_groups, total_tiles, ep, out_planes, stream);
-    default: return launch_gemm_tc_f<BN, NSPLIT, F_GENERIC>(table, n_groups, total_tiles, ep, out_planes, stream);
+    case F_PLAIN: return launch_gemm_tc_f<BN, NSPLIT, F_PLAIN, CG>(table, n_groups, total_tiles, ep, out_planes, stream);
+    case F_ROT: return launch_gemm_tc_f<BN, NSPLIT, F_ROT, CG>(table, n_groups, total_tiles, ep, out_planes, stream);
+    case F_GELU: return launch_gemm_tc_f<BN, NSPLIT, F_GELU, CG>(table, n_groups, total_tiles, ep, out_planes, stream);
+    case F_TANH: return launch_gemm_tc_f<BN, NSPLIT, F_TANH, CG>(table, n_groups, total_tiles, ep, out_planes, stream);
+    case F_GLU: return launch_gemm_tc_f<BN, NSPLIT, F_GLU, CG>(table, n_groups, total_tiles, ep, out_planes, stream);
+    default: return launch_gemm_tc_f<BN, NSPLIT, F_GENERIC, CG>(table, n_groups, total_tiles, ep, out_planes, stream);
   }
 }
 
@@ -545,8 +629,9 @@ int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint
 
 extern "C" int64_t sesa_gemm_tc_table_bytes(int n_groups) { return (int64_t)sizeof(TcGroup) * (n_groups > 0 ? n_groups : 0); }
 
-extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int block_n, void* table_host,
+extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int block_n, int cta_group, void* table_host,
                                   int* total_tiles) {
+  SESA_CHECK_ARG(cta_group == 1 || (cta_group == 2 && block_n == 256), "sesa_gemm_tc_build: cta_group must be 1, or 2 with block_n 256");
   SESA_CHECK_ARG(pr != nullptr && table_host != nullptr && total_tiles != nullptr, "sesa_gemm_tc_build: null argument");
   SESA_CHECK_ARG(n_groups > 0 && n_groups <= MAX_GROUPS, "sesa_gemm_tc_build: group count %d out of range", n_groups);
   SESA_CHECK_ARG(block_n == 128 || block_n == 256, "sesa_gemm_tc_build: block_n must be 128 or 256");
@@ -607,7 +692,7 @@ extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int b
     g.rm_df = p.rm_df;
     const uint64_t dimsW[3] = {(uint64_t)p.K, (uint64_t)p.N, 2};
     const uint64_t strW[2] = {(uint64_t)p.ldw * 2, (uint64_t)(p.w_plane > 0 ? p.w_plane : p.ldw * (int64_t)p.N) * 2};
-    const uint32_t boxW[3] = {BK, (uint32_t)block_n, 1};
+    const uint32_t boxW[3] = {BK, (uint32_t)(block_n / cta_group), 1};   // each CTA of a pair stages half of the W tile
     rc = sesa_make_tmap_bf16(&g.mapW, p.W, 3, dimsW, strW, boxW);
     if (rc != SESA_OK) return rc;
     g.bias = p.bias;
@@ -633,7 +718,7 @@ extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int b
     g.n_blocks = (p.N + block_n - 1) / block_n;
     g.k_blocks = (p.K + BK - 1) / BK;
     g.tile_begin = tiles;
-    tiles += ((p.M + BM - 1) / BM) * g.n_blocks;
+    tiles += ((p.M + BM * cta_group - 1) / (BM * cta_group)) * g.n_blocks;
     g.tile_end = tiles;
     memcpy(&tab[i], &g, sizeof(g));
   }
@@ -641,8 +726,9 @@ extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int b
   return SESA_OK;
 }
 
-extern "C" int sesa_gemm_tc(const void* table_dev, int n_groups, int total_tiles, int block_n, int nsplit,
+extern "C" int sesa_gemm_tc(const void* table_dev, int n_groups, int total_tiles, int block_n, int cta_group, int nsplit,
                             int out_planes, const sesa_gemm_epilogue* ep, void* stream) {
+  SESA_CHECK_ARG(cta_group == 1 || (cta_group == 2 && block_n == 256), "sesa_gemm_tc: cta_group must be 1, or 2 with block_n 256");
   SESA_CHECK_ARG(table_dev != nullptr && ep != nullptr, "sesa_gemm_tc: null argument");
   SESA_CHECK_ARG(n_groups > 0 && n_groups <= MAX_GROUPS, "sesa_gemm_tc: group count %d out of range", n_groups);
   SESA_CHECK_ARG(nsplit == 1 || nsplit == 3, "sesa_gemm_tc: nsplit must be 1 or 3");
@@ -655,10 +741,12 @@ extern "C" int sesa_gemm_tc(const void* table_dev, int n_groups, int total_tiles
   if (total_tiles <= 0) return SESA_OK;
   const TcGroup* tab = reinterpret_cast<const TcGroup*>(table_dev);
   cudaStream_t st = (cudaStream_t)stream;
-  if (block_n == 256 && nsplit == 3) return launch_gemm_tc<256, 3>(tab, n_groups, total_tiles, *ep, out_planes, st);
-  if (block_n == 256 && nsplit == 1) return launch_gemm_tc<256, 1>(tab, n_groups, total_tiles, *ep, out_planes, st);
-  if (block_n == 128 && nsplit == 3) return launch_gemm_tc<128, 3>(tab, n_groups, total_tiles, *ep, out_planes, st);
-  if (block_n == 128 && nsplit == 1) return launch_gemm_tc<128, 1>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  if (cta_group == 2 && nsplit == 3) return launch_gemm_tc<256, 3, 2>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  if (cta_group == 2 && nsplit == 1) return launch_gemm_tc<256, 1, 2>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  if (block_n == 256 && nsplit == 3) return launch_gemm_tc<256, 3, 1>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  if (block_n == 256 && nsplit == 1) return launch_gemm_tc<256, 1, 1>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  if (block_n == 128 && nsplit == 3) return launch_gemm_tc<128, 3, 1>(tab, n_groups, total_tiles, *ep, out_planes, st);
+  if (block_n == 128 && nsplit == 1) return launch_gemm_tc<128, 1, 1>(tab, n_groups, total_tiles, *ep, out_planes, st);
   sesa_set_error("sesa_gemm_tc: unsupported block_n %d", block_n);
   return SESA_ERR_UNSUPPORTED;
 }

@@ -53,6 +53,11 @@ def prep_rows(x, rows, dim, ldx, planes, normalize, gate_w=None, gate_b=None, ga
          _stream())
 
 
+# CTA pairs (tcgen05 cta_group::2, 256 x 256 pair tiles) are the default for the 256-wide tile: they halve the W-tile
+# traffic and reach 1.2-1.55 PFLOP/s of issued MMA where single-CTA tiles stall on L2 (profiles/r1_microbench.md)
+DEFAULT_CTA_GROUP = 2
+
+
 class TcGemmTable:
     """Device table of one (grouped) sesa_gemm_tc launch.
 
@@ -60,7 +65,9 @@ class TcGemmTable:
     optional bias, rowscale, C (ptr, ldc), P (ptr, ldp, plane_stride).
     """
 
-    def __init__(self, problems, device, block_n=256):
+    def __init__(self, problems, device, block_n=256, cta_group=None):
+        if cta_group is None:
+            cta_group = DEFAULT_CTA_GROUP if block_n == 256 else 1
         n = len(problems)
         arr = np.zeros(n, dtype=TC_PROBLEM_DTYPE)
         for i, p in enumerate(problems):
@@ -91,14 +98,14 @@ class TcGemmTable:
         nbytes = int(lib.sesa_gemm_tc_table_bytes(n))
         host = np.zeros(nbytes, dtype=np.uint8)
         tiles = ctypes.c_int(0)
-        _lib.check(lib.sesa_gemm_tc_build(arr.ctypes.data_as(ctypes.c_void_p), n, block_n,
+        _lib.check(lib.sesa_gemm_tc_build(arr.ctypes.data_as(ctypes.c_void_p), n, block_n, cta_group,
                                           host.ctypes.data_as(ctypes.c_void_p), ctypes.byref(tiles)))
-        self.n, self.block_n, self.tiles = n, block_n, int(tiles.value)
+        self.n, self.block_n, self.cta_group, self.tiles = n, block_n, cta_group, int(tiles.value)
         self.dev = torch.from_numpy(host).to(device)
         self.flops = sum(2 * int(p['M']) * int(p['N']) * int(p['K']) for p in problems)
 
     def run(self, ep, nsplit=3, out_planes=2):
-        call('sesa_gemm_tc', _ptr(self.dev), self.n, self.tiles, self.block_n, nsplit, out_planes, ctypes.byref(ep),
+        call('sesa_gemm_tc', _ptr(self.dev), self.n, self.tiles, self.block_n, self.cta_group, nsplit, out_planes, ctypes.byref(ep),
              _stream())
 
 

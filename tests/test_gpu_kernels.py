@@ -200,7 +200,7 @@ def _bf16_round(x):
 
 
 def _tc_case(lib, M, N, K, nsplit, block_n, bias=True, act=0, rowscale=False, residual=False, glu=False, rot=None,
-             planes_out=False, seed=0):
+             planes_out=False, seed=0, cg=1):
     from sesa_audio_separation_b200 import tc
     from sesa_audio_separation_b200._lib import GemmEpilogue
     dev = 'cuda'
@@ -224,7 +224,7 @@ def _tc_case(lib, M, N, K, nsplit, block_n, bias=True, act=0, rowscale=False, re
     prob = dict(A=tc.planes_arg(ap), W=tc.planes_arg(wp), M=M, N=N, K=K, bias=bd.data_ptr() if bias else 0,
                 rowscale=rsd.data_ptr() if rowscale else 0, C=(cd.data_ptr(), ldc),
                 P=tc.planes_arg(pout) if planes_out else None)
-    tab = tc.TcGemmTable([prob], dev, block_n=block_n)
+    tab = tc.TcGemmTable([prob], dev, block_n=block_n, cta_group=cg if block_n == 256 else 1)
     rot_d = None
     ep = GemmEpilogue(0, act, 1 if residual else 0, 1 if glu else 0, 0, 0, 1, 1, None)
     if rot is not None:
@@ -281,15 +281,24 @@ def test_gemm_tc_plain(lib, nsplit, block_n):
         assert err < (3e-5 if nsplit == 3 else 2e-5), (M, N, K, err)   # bf16 mode is compared with bf16-rounded operands
 
 
-def test_gemm_tc_ragged_and_epilogues(lib):
-    # ragged N / K tails (mask-estimator and band-split shapes), every epilogue
-    assert _tc_case(lib, 801, 16, 2048, 3, 256, act=0, glu=True) < 3e-5
-    assert _tc_case(lib, 801, 1032, 2048, 3, 256, glu=True, seed=3) < 3e-5
-    assert _tc_case(lib, 333, 96, 520, 3, 128, act=2, seed=4) < 3e-5
-    assert _tc_case(lib, 640, 2048, 512, 3, 256, act=1, rowscale=True, planes_out=True, seed=5) < 3e-5
-    assert _tc_case(lib, 640, 512, 2048, 3, 256, residual=True, planes_out=True, seed=6) < 3e-5
-    assert _tc_case(lib, 62 * 9, 1536, 512, 3, 256, bias=False, rot=(1024, 64, 62, 9), planes_out=True, seed=7) < 3e-5
-    assert _tc_case(lib, 200, 24, 8, 3, 256, seed=8) < 3e-5
+@pytest.mark.parametrize('cg', [1, 2])
+def test_gemm_tc_ragged_and_epilogues(lib, cg):
+    # ragged N / K tails (mask-estimator and band-split shapes), every epilogue; cg = 2: CTA pairs (cta_group::2)
+    assert _tc_case(lib, 801, 16, 2048, 3, 256, act=0, glu=True, cg=cg) < 3e-5
+    assert _tc_case(lib, 801, 1032, 2048, 3, 256, glu=True, seed=3, cg=cg) < 3e-5
+    assert _tc_case(lib, 333, 96, 520, 3, 128 if cg == 1 else 256, act=2, seed=4, cg=cg) < 3e-5
+    assert _tc_case(lib, 640, 2048, 512, 3, 256, act=1, rowscale=True, planes_out=True, seed=5, cg=cg) < 3e-5
+    assert _tc_case(lib, 640, 512, 2048, 3, 256, residual=True, planes_out=True, seed=6, cg=cg) < 3e-5
+    assert _tc_case(lib, 62 * 9, 1536, 512, 3, 256, bias=False, rot=(1024, 64, 62, 9), planes_out=True, seed=7, cg=cg) < 3e-5
+    assert _tc_case(lib, 200, 24, 8, 3, 256, seed=8, cg=cg) < 3e-5
+
+
+@pytest.mark.parametrize('nsplit', [3, 1])
+def test_gemm_tc_cta_pairs(lib, nsplit):
+    for (M, N, K) in [(128, 256, 64), (300, 512, 512), (1000, 1544, 512), (257, 2048, 128), (513, 512, 2048), (5000, 1024, 512)]:
+        err = _tc_case(lib, M, N, K, nsplit, 256, seed=M, cg=2)
+        print('gemm_tc 2-CTA', M, N, K, nsplit, err)
+        assert err < (3e-5 if nsplit == 3 else 2e-5), (M, N, K, err)
 
 
 def test_gemm_tc_grouped(lib):

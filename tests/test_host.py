@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/sesa_b200.h but not exported'
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.sesa_abi_version() == 1
+    assert lib.sesa_abi_version() == 2
 
 
 def test_plan_matches_oracle_schedule():

@@ -20,6 +20,7 @@ def main():
     ap.add_argument('--nsplit', type=int, default=3)
     ap.add_argument('--block-n', type=int, default=256)
     ap.add_argument('--only', default='')
+    ap.add_argument('--cta-group', type=int, default=2)
     args = ap.parse_args()
     _lib.require_cuda()
     dev = 'cuda'
@@ -44,7 +45,7 @@ def main():
     rot = torch.stack([ang.cos(), ang.sin()], -1).contiguous().to(dev)
 
     def table(A, W, N, K, **kw):
-        return tc.TcGemmTable([dict(A=tc.planes_arg(A), W=tc.planes_arg(W), M=M, N=N, K=K, **kw)], dev, block_n=args.block_n)
+        return tc.TcGemmTable([dict(A=tc.planes_arg(A), W=tc.planes_arg(W), M=M, N=N, K=K, **kw)], dev, block_n=args.block_n, cta_group=args.cta_group)
     cases = {
         'qkv': (table(xp, w['qkv'], 1536, 512, C=(qkv.data_ptr(), 1544)),
                 GemmEpilogue(0, 0, 0, 0, 1024, 64, 62, 801, rot.data_ptr()), 2 * M * 1536 * 512),
@@ -76,7 +77,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.reps
-        print(f'{name:6s} M={M} nsplit={args.nsplit} BN={args.block_n}: {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s algorithmic '
+        print(f'{name:6s} M={M} nsplit={args.nsplit} BN={args.block_n} CG={args.cta_group}: {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s algorithmic '
               f'({flops * (3 if args.nsplit == 3 else 1) / ms / 1e9:8.1f} MMA TFLOP/s)')
 
 
