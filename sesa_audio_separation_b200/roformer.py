@@ -410,7 +410,8 @@ class _RoformerBase(KernelModule):
 
     def _refresh_planes(self, ws):
         """(Re)build the bf16 planes and row sums of squares of the residual stream after a non-GEMM producer."""
-        tc.prep_rows(ws['x'], ws['M'], self.dim, self.dim, ws['xp'], 2, rowinv=ws['ss'], ss_slots=ws['ss_slots'])
+        tc.prep_rows(ws['x'], ws['M'], self.dim, self.dim, ws['xp'], 2, rowinv=ws['ss'], ss_slots=ws['ss_slots'],
+                     out_planes=2 if self.precision == 'fp32' else 1)
 
     def _transformer(self, ws, prep, gl, tr, axis, B, tgl=None):
         T, nb, D, H = ws['T'], self.num_bands, self.dim, self.heads
@@ -422,6 +423,7 @@ class _RoformerBase(KernelModule):
             n_seq, seq_len, inner_cnt, outer, inner_s, pos_s = B * T, nb, 1, nb, 0, 1
             pos_div, pos_mod = 1, nb
         nsplit = 3 if self.precision == 'fp32' else 1
+        npl = 2 if nsplit == 3 else 1      # bf16 mode never reads the lo planes: do not write them either
         for si, (s, g) in enumerate(zip(tr['subs'], gl)):
             rot = self._rot_table(prep, s['freqs'], seq_len)
             if self._tc:
@@ -430,14 +432,14 @@ class _RoformerBase(KernelModule):
                 # xp holds the raw residual stream as bf16 planes and ss its row sums of squares (both written by the
                 # previous residual epilogue): RMSNorm is the consumer's row scale, gamma*sqrt(D) lives in the weights
                 t['qkv'].run(_epilogue(rot=rot, rot_cols=2 * inner, rot_dim=self.dim_head, pos_div=pos_div,
-                                       pos_mod=pos_mod), nsplit)
+                                       pos_mod=pos_mod), nsplit, npl)
                 qp, ap = ws['qkvp'], ws['aop']
                 call('sesa_attention_tc', _ptr(qp), qp.shape[-1], qp.stride(0), _ptr(ws['gates']), 8, _ptr(ap),
                      ap.shape[-1], ap.stride(0), H, self.dim_head, n_seq, seq_len, inner_cnt, outer, inner_s, pos_s,
-                     T if axis == 1 else 0, nsplit, 2, _stream())
-                t['out'].run(_epilogue(residual=1), nsplit)
-                t['ff1'].run(_epilogue(act=_lib.ACT_GELU), nsplit)
-                t['ff2'].run(_epilogue(residual=1), nsplit)
+                     T if axis == 1 else 0, nsplit, npl, _stream())
+                t['out'].run(_epilogue(residual=1), nsplit, npl)
+                t['ff1'].run(_epilogue(act=_lib.ACT_GELU), nsplit, npl)
+                t['ff2'].run(_epilogue(residual=1), nsplit, npl)
                 continue
             self._gemm(g['qkv'], _epilogue(rownorm=1, rot=rot, rot_cols=2 * self.inner, rot_dim=self.dim_head,
                                            pos_div=pos_div, pos_mod=pos_mod))
@@ -491,7 +493,8 @@ class _RoformerBase(KernelModule):
         for li in range(nl):
             last = li == nl - 1
             if self._tc:
-                ws['t_mask'][li].run(_epilogue(act=0 if last else _lib.ACT_TANH, glu=1 if last else 0), nsplit)
+                ws['t_mask'][li].run(_epilogue(act=0 if last else _lib.ACT_TANH, glu=1 if last else 0), nsplit,
+                                     2 if nsplit == 3 else 1)
                 continue
             self._gemm(ws['g_mask'][li], _epilogue(rownorm=1 if (li == 0 and self.has_final_norm) else 0,
                                                     act=0 if last else _lib.ACT_TANH, glu=1 if last else 0))

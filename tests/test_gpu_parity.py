@@ -207,3 +207,15 @@ def test_cli_inference_end_to_end(tmp_path, capsys):
     ins, _ = load_audio(str(outdir / 'song.wav_instrumental.wav'), 44100)
     assert np.array_equal(voc, ref)
     assert np.allclose(ins, mix - ref, atol=1e-7)
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_bf16_mode_snr_gate(name):
+    """bf16 mode of BASELINE.json (single bf16 MMA per product, fp32 accumulate): SNR >= 40 dB vs the reference goldens."""
+    case = CASES[name]
+    model, _ = build(case)
+    model.set_precision('bf16')
+    y = model(make_input(case).cuda()).cpu().numpy()
+    ref = golden(name)['y']
+    print(name, 'bf16 mode: max_rel', max_rel(ref, y), 'snr', snr_db(ref, y))
+    assert snr_db(ref, y) >= 40.0
