@@ -43,6 +43,17 @@ struct AttnParams {
   int out_planes;
 };
 
+// 64-thread named barrier of the warp pair (w, w+4) that shares a TMEM lane quadrant (ids 1..4, compile-time ids keep
+// the kernel's barrier count at 5)
+__device__ __forceinline__ void pair_barrier(int quadrant) {
+  switch (quadrant) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
 template <int NSPLIT>
 struct ACfg {
   static constexpr int NP = NSPLIT == 3 ? 2 : 1;
@@ -262,35 +273,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       tc::tmem_ld32(tmem_SP + st * 64 + lane_off + hf * HC, s);
       tc::tmem_ld_wait();
       const int k0 = j * BKV + hf * HC;
-      float mx = -INFINITY;
+      float mx = -INFINITY;     // row maximum of the RAW scores; the log2(e) factor is folded into the exp2 argument FMA
       if (__all_sync(0xffffffffu, k0 >= lo && k0 + HC <= hi)) {
 #pragma unroll
-        for (int c = 0; c < HC; ++c) {
-          s[c] *= LOG2E;
-          mx = fmaxf(mx, s[c]);
-        }
+        for (int c = 0; c < HC; ++c) mx = fmaxf(mx, s[c]);
       } else {
 #pragma unroll
         for (int c = 0; c < HC; ++c) {
           const int kj = k0 + c;
-          s[c] = (kj >= lo && kj < hi) ? s[c] * LOG2E : -INFINITY;
+          s[c] = (kj >= lo && kj < hi) ? s[c] : -INFINITY;
           mx = fmaxf(mx, s[c]);
         }
       }
       float* xm = xch + (st * 2) * BQ;
       xm[hf * BQ + i] = mx;
       tc::tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // also: both halves of every row have read their scores
+      // the two threads of a row sit in warps w and w+4: a 64-thread named barrier per warp pair (also orders
+      // "both halves of every row have read their scores" before P overwrites them in place)
+      pair_barrier(warp & 3);
       tc::tc_fence_after();
       const float mnew = fmaxf(mrun, fmaxf(mx, xm[(hf ^ 1) * BQ + i]));
-      const float moff = mnew == -INFINITY ? 0.f : mnew;
-      const float corr = tc::ex2_approx(mrun - moff);
+      const float moff = (mnew == -INFINITY ? 0.f : mnew) * LOG2E;
+      const float corr = tc::ex2_approx(fmaf(mrun, LOG2E, -moff));
       float sum = 0.f;
       uint32_t phi[HC / 2], plo[HC / 2];
 #pragma unroll
       for (int e = 0; e < HC / 2; ++e) {
-        const float p0 = tc::ex2_approx(s[2 * e] - moff);
-        const float p1 = tc::ex2_approx(s[2 * e + 1] - moff);
+        const float p0 = tc::ex2_approx(fmaf(s[2 * e], LOG2E, -moff));
+        const float p1 = tc::ex2_approx(fmaf(s[2 * e + 1], LOG2E, -moff));
         sum += p0 + p1;
         tc::split_bf16x2(p0, p1, phi[e], plo[e]);
       }
@@ -309,7 +319,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
     // combine the two halves' row sums, gate, split to planes, store this thread's 32 output dims
     float* xs = xch + ((nblk & 1) * 2) * BQ;
     xs[hf * BQ + i] = lrun;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    pair_barrier(warp & 3);
     const float ltot = lrun + xs[(hf ^ 1) * BQ + i];
     if (row_valid) {
       const float gl = p.gates[out_row * p.ldg + h];
