@@ -99,6 +99,34 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def secondary_rooflines(prof, n_chunks, att_f, tf_peak, hbm_peak, seconds, mma_mult):
+    """Achieved rate of every other kernel class against the roofline that bounds it (SURVEY 8d byte/FLOP figures)."""
+    T, F, C, N, L = 1 + CHUNK // 441, 1025, 2, 1, CHUNK
+    per_chunk_bytes = {
+        'stft': 4 * C * L + 8 * C * F * T,                               # audio read + spectrogram write
+        'mask_istft': 8 * C * F * T + 8 * N * C * F * T + 4 * N * C * L,  # spec + mask read, chunk output write
+        'framing': 2 * 4 * C * L,                                         # chunk gather (read + write)
+    }
+    out = {}
+    for k, b in per_chunk_bytes.items():
+        n, ms = prof.get(k, (0, 0.0))
+        if ms > 0:
+            gbs = b * n_chunks / 1e9 / (ms / 1e3)
+            out[k] = {'bound': 'hbm', 'ms_per_step': round(ms, 3), 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                      'frac': gbs / hbm_peak}
+    n, ms = prof.get('overlap_add', (0, 0.0))
+    if ms > 0:
+        b = 4 * N * C * L * n_chunks + 4 * N * C * int(seconds * SR)
+        out['overlap_add'] = {'bound': 'hbm', 'ms_per_step': round(ms, 3), 'achieved': b / 1e9 / (ms / 1e3), 'peak': hbm_peak,
+                              'unit': 'GB/s', 'frac': b / 1e9 / (ms / 1e3) / hbm_peak}
+    n, ms = prof.get('attention', (0, 0.0))
+    if ms > 0:
+        tf = att_f * n_chunks / 1e12 / (ms / 1e3)
+        out['attention'] = {'bound': 'tensor', 'ms_per_step': round(ms, 3), 'achieved': tf, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                            'frac': tf / tf_peak, 'mma_frac_of_peak': tf * mma_mult / tf_peak}
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -267,6 +295,7 @@ def main():
                                  if mma_mult == 3 else '',
                          'share_of_step': gemm_ms / max(1e-9, sum(t for _, t in prof.values()))},
             'breakdown_ms_per_step': breakdown, 'attention_tflop_per_chunk': att_f / 1e12,
+            'kernels': secondary_rooflines(prof, n_chunks, att_f, tf_peak, hbm_peak, args.seconds, mma_mult),
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(model.state_dict(), 1, 0)

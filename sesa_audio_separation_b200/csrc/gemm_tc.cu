@@ -336,6 +336,33 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       tc::mbar_wait(&tmem_full[as], aph);
       tc::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + ch * HALF;
+      // software-pipelined per-step constants: the bias quad of this lane's 4 columns and, for rotary columns, the
+      // (cos, sin) quads of its 4 rows are fetched one 16-column step ahead so their latency hides under the current step
+      float4 b4_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 cs_next[4];
+      auto load_step_constants = [&](int cstep) {
+        const int nn = n_half + cstep * EPI_COLS;
+        const int cb = nn + c4 * 4;
+        b4_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cstep < HALF / EPI_COLS && nn < N) {
+          if (bias != nullptr) {
+            if (vec_ok && nn + EPI_COLS <= N) b4_next = __ldg(reinterpret_cast<const float4*>(bias + cb));
+            else {
+              if (cb < N) b4_next.x = bias[cb];
+              if (cb + 1 < N) b4_next.y = bias[cb + 1];
+              if (cb + 2 < N) b4_next.z = bias[cb + 2];
+              if (cb + 3 < N) b4_next.w = bias[cb + 3];
+            }
+          }
+          if (nn < rot_cols) {
+            const int rd = (cb % ep.rot_dim) >> 1;
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+              cs_next[it] = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rd) >> 1));
+          }
+        }
+      };
+      load_step_constants(0);
 #pragma unroll 1
       for (int c = 0; c < HALF / EPI_COLS; ++c) {
         const int n = n_half + c * EPI_COLS;
@@ -351,20 +378,14 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             sts128(stage + lane * (EPI_COLS * 4) + ((j4 ^ ((lane >> 1) & 3)) << 4),
                    make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
         }
-        // per-lane constants of this step: bias quad (same columns for all 4 rows)
+        // per-lane constants of this step (bias quad, rotary quads) were loaded one step ahead; fetch the next step's now
         const bool interior = vec_ok && n + EPI_COLS <= N;   // warp-uniform: no ragged right edge in this step
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias != nullptr) {
-          if (interior) b4 = __ldg(reinterpret_cast<const float4*>(bias + colb));
-          else {
-            if (colb < N) b4.x = bias[colb];
-            if (colb + 1 < N) b4.y = bias[colb + 1];
-            if (colb + 2 < N) b4.z = bias[colb + 2];
-            if (colb + 3 < N) b4.w = bias[colb + 3];
-          }
-        }
+        const float4 b4 = b4_next;
         const bool do_rot = n < rot_cols;
-        const int rot_d = do_rot ? ((colb % ep.rot_dim) >> 1) : 0;   // first of the two (cos, sin) pairs of this quad
+        float4 cs4[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) cs4[it] = cs_next[it];
+        load_step_constants(c + 1);
         float4 res[4];
         if (ep.residual && interior) {   // issue the residual reads before the shared-memory round trip completes
 #pragma unroll
@@ -410,7 +431,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
           if (do_rot) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-              const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rot_d) >> 1));
+              const float4 cs = cs4[it];
               const float x1 = o[it].x, x2 = o[it].y, x3 = o[it].z, x4 = o[it].w;
               o[it].x = x1 * cs.x - x2 * cs.y;
               o[it].y = x2 * cs.x + x1 * cs.y;
@@ -458,7 +479,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               o.z = 1.0f / (1.0f + expf(-o.z)); o.w = 1.0f / (1.0f + expf(-o.w));
             }
             if (do_rot) {
-              const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rot_d) >> 1));
+              const float4 cs = cs4[it];
               const float x1 = o.x, x2 = o.y, x3 = o.z, x4 = o.w;
               o.x = x1 * cs.x - x2 * cs.y;
               o.y = x2 * cs.x + x1 * cs.y;

@@ -40,16 +40,38 @@ __global__ void __launch_bounds__(256) instnorm_acc_kernel(const float* __restri
   const int64_t i0 = (int64_t)blockIdx.x * chunk;
   const int64_t i1 = min(n1, i0 + chunk);
   if (layout == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float s = 0.f, ss = 0.f;
-      const float* p = x + ((int64_t)b * n1 + i0) * ld + c;
-      for (int64_t i = i0; i < i1; ++i, p += ld) {
-        const float v = *p;
-        s += v;
-        ss = fmaf(v, v, ss);
+    // threads = (channel quads) x (position lanes): float4 loads, 512 contiguous bytes per warp and position
+    __shared__ float red[256][8];
+    const int cq = C >> 2;                               // C % 4 == 0 (checked by the host entry)
+    const int nq = cq < 256 ? cq : 256;                  // channel quads handled per pass
+    const int lanes = 256 / nq;                          // position lanes
+    const int tq = threadIdx.x % nq, tl = threadIdx.x / nq;
+    for (int q0 = 0; q0 < cq; q0 += nq) {
+      const int qd = q0 + tq;
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+      if (qd < cq && tl < lanes) {
+        const float* p = x + ((int64_t)b * n1 + i0 + tl) * ld + 4 * qd;
+        for (int64_t i = i0 + tl; i < i1; i += lanes, p += (int64_t)lanes * ld) {
+          const float4 v = *reinterpret_cast<const float4*>(p);
+          s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+          ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]);
+          ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
+        }
       }
-      atomicAdd(&acc[((int64_t)b * C + c) * 2], (double)s);
-      atomicAdd(&acc[((int64_t)b * C + c) * 2 + 1], (double)ss);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { red[threadIdx.x][e] = s[e]; red[threadIdx.x][4 + e] = ss[e]; }
+      __syncthreads();
+      if (tl == 0 && qd < cq) {
+        for (int l = 1; l < lanes; ++l)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { s[e] += red[l * nq + tq][e]; ss[e] += red[l * nq + tq][4 + e]; }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          atomicAdd(&acc[((int64_t)b * C + 4 * qd + e) * 2], (double)s[e]);
+          atomicAdd(&acc[((int64_t)b * C + 4 * qd + e) * 2 + 1], (double)ss[e]);
+        }
+      }
+      __syncthreads();
     }
   } else {
     // one warp per (i, c) row of n2 contiguous values
@@ -107,16 +129,19 @@ __global__ void __launch_bounds__(256) norm_act_split_kernel(const float* __rest
     if (mode == 0) {
       const int64_t b = r / n1;
       v = *reinterpret_cast<const float4*>(x + r * ld + q);
-      const float in[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float y = in[e];
-        if (stats != nullptr) {
-          const float2 st = stats[b * C + q + e];
-          y = (y - st.x) * st.y * gamma[q + e] + beta[q + e];
-        }
-        o[e] = apply_act(y, act);
+      float in[4] = {v.x, v.y, v.z, v.w};
+      if (stats != nullptr) {   // (mean, rstd) pairs, gamma and beta of the quad's 4 channels: four 16-byte loads
+        const float4 s01 = __ldg(reinterpret_cast<const float4*>(stats + b * C + q));
+        const float4 s23 = __ldg(reinterpret_cast<const float4*>(stats + b * C + q + 2));
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + q));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + q));
+        in[0] = (in[0] - s01.x) * s01.y * g4.x + b4.x;
+        in[1] = (in[1] - s01.z) * s01.w * g4.y + b4.y;
+        in[2] = (in[2] - s23.x) * s23.y * g4.z + b4.z;
+        in[3] = (in[3] - s23.z) * s23.w * g4.w + b4.w;
       }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = apply_act(in[e], act);
     } else {
       const int64_t bc = r;                 // row index = (b*n1 + i)*C + c
       const int c = (int)(bc % C);
@@ -264,9 +289,11 @@ extern "C" int sesa_instnorm_stats(const float* x, int layout, int batch, int64_
                                    double* scratch, float* stats, float eps, void* stream) {
   SESA_CHECK_ARG(layout == 0 || layout == 1, "sesa_instnorm_stats: layout must be 0 or 1");
   SESA_CHECK_ARG(batch > 0 && n1 > 0 && channels > 0 && n2 > 0, "sesa_instnorm_stats: empty tensor");
+  SESA_CHECK_ARG(layout != 0 || ((channels & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0),
+                 "sesa_instnorm_stats: channels-last statistics need channels % 4 == 0 and 16-byte aligned rows");
   cudaStream_t st = (cudaStream_t)stream;
   SESA_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)batch * channels, st));
-  const int64_t chunk = layout == 0 ? 128 : 4;
+  const int64_t chunk = layout == 0 ? 256 : 4;
   dim3 grid((unsigned)ceil_div64(n1, chunk), batch);
   instnorm_acc_kernel<<<grid, 256, 0, st>>>(x, layout, batch, n1, channels, n2, ld, chunk, scratch);
   SESA_LAUNCH_CHECK();
