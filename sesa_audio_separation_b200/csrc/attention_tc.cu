@@ -40,6 +40,7 @@ struct AttnParams {
   int spt;              // packed: sequences per tile
   int seq_group;        // packed: sequences are packed within groups of this many (one group per chunk), so a
   int tiles_per_group;  //         sequence's arithmetic never depends on the batch it is launched in
+  int q_tiles;          // strided: 128-row query tiles per sequence
   int out_planes;
 };
 
@@ -95,7 +96,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int h = blockIdx.z;
+  // flat grid, heads fastest: the CTAs of the 8 heads of one row tile run together, so the 256-byte L2 fetches around
+  // each 128-byte head slice are shared instead of being fetched twice from HBM
+  const int h = blockIdx.x % p.heads;
+  const int item = blockIdx.x / p.heads;
 
   if (tid == SM_THREADS) {
     tc::mbar_init(q_full, 1);
@@ -126,14 +130,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
   int c1 = 0, c3 = 0;          // TMA coordinates that stay fixed (strided: f and b)
   int64_t row_base = 0;        // packed: first row of the tile
   if (p.mode == 0) {
-    const int seq = blockIdx.y;
-    q0 = blockIdx.x * BQ;
+    const int seq = item / p.q_tiles;
+    q0 = (item - seq * p.q_tiles) * BQ;
     c1 = seq % p.inner_cnt;
     c3 = seq / p.inner_cnt;
     nblk = (p.seq_len + BKV - 1) / BKV;
   } else {
-    const int grp = blockIdx.x / p.tiles_per_group;
-    const int lt = blockIdx.x - grp * p.tiles_per_group;
+    const int grp = item / p.tiles_per_group;
+    const int lt = item - grp * p.tiles_per_group;
     row_base = ((int64_t)grp * p.seq_group + (int64_t)lt * p.spt) * p.seq_len;
     nblk = BQ / BKV;
   }
@@ -239,8 +243,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       out_row = (int64_t)c3 * p.outer_stride + (int64_t)c1 * p.inner_stride + (int64_t)(q0 + i) * p.pos_stride;
     } else {
       const int sl = i / p.seq_len;
-      const int grp = blockIdx.x / p.tiles_per_group;
-      const int lseq = (blockIdx.x - grp * p.tiles_per_group) * p.spt + sl;   // sequence index inside its group
+      const int grp = item / p.tiles_per_group;
+      const int lseq = (item - grp * p.tiles_per_group) * p.spt + sl;   // sequence index inside its group
       row_valid = sl < p.spt && lseq < p.seq_group && (int64_t)grp * p.seq_group + lseq < p.n_seq;
       lo = row_valid ? sl * p.seq_len : 0;
       hi = row_valid ? lo + p.seq_len : 0;
@@ -389,6 +393,7 @@ extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t pla
   p.spt = 1;
   p.seq_group = n_seq;
   p.tiles_per_group = 1;
+  p.q_tiles = 1;
   CUtensorMap map;
   dim3 grid;
   const bool packed = pos_stride == 1 && seq_len <= BKV && inner_cnt == 1 && outer_stride == seq_len;
@@ -406,7 +411,7 @@ extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t pla
     const uint32_t boxp[5] = {64, 64, 1, 1, 1};
     int rc = sesa_make_tmap_bf16(&map, qkv_planes, 5, dims, str, boxp);
     if (rc != SESA_OK) return rc;
-    grid = dim3((unsigned)((n_seq / p.seq_group) * p.tiles_per_group), 1, heads);
+    grid = dim3((unsigned)((int64_t)(n_seq / p.seq_group) * p.tiles_per_group * heads), 1, 1);
   } else {
     // sequence s = (b, f): row = b*outer + f*inner + pos*pos_stride
     p.mode = 0;
@@ -417,8 +422,9 @@ extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t pla
                              (uint64_t)outer_stride * ld * 2, (uint64_t)plane_stride * 2};
     int rc = sesa_make_tmap_bf16(&map, qkv_planes, 5, dims, str, box);
     if (rc != SESA_OK) return rc;
-    SESA_CHECK_ARG(n_seq <= 65535, "sesa_attention_tc: too many sequences for one launch (%d)", n_seq);
-    grid = dim3((unsigned)((seq_len + BQ - 1) / BQ), (unsigned)n_seq, heads);
+    p.q_tiles = (seq_len + BQ - 1) / BQ;
+    SESA_CHECK_ARG((int64_t)n_seq * p.q_tiles * heads < (1LL << 31), "sesa_attention_tc: too many tiles for one launch");
+    grid = dim3((unsigned)((int64_t)n_seq * p.q_tiles * heads), 1, 1);
   }
   if (nsplit == 3) return launch_attention_tc<3>(map, p, grid, (cudaStream_t)stream);
   return launch_attention_tc<1>(map, p, grid, (cudaStream_t)stream);
