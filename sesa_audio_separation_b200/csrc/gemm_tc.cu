@@ -307,16 +307,32 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       int pos4[4];
       bool ok4[4];
       float ssq[4] = {0.f, 0.f, 0.f, 0.f};
+      const int mm0 = m_base + rb;
+      // sequence position of row mm0 (rotary): one division per tile, the other three rows follow incrementally
+      int pos_q = 0, pos_r = 0;
+      if (rot_cols > 0) {
+        const int qd = mm0 / ep.pos_div;
+        pos_r = mm0 - qd * ep.pos_div;
+        pos_q = qd % ep.pos_mod;
+      }
+      const float* __restrict__ rowss = g->rowss;
+      const int ss_slots = g->ss_slots;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int mm = m_base + it * 8 + rb;
+        const int mm = mm0 + it * 8;
         ok4[it] = mm < M;
         float r = 1.0f;
         if (ok4[it]) {
           if (g->rowscale != nullptr) r = g->rowscale[mm];
-          if (g->rowss != nullptr) {   // fused RMSNorm: F.normalize(x, dim=-1) of the GEMM input (bs_roformer.py:49)
-            float ssum = 0.f;
-            for (int k = 0; k < g->ss_slots; ++k) ssum += g->rowss[(int64_t)mm * g->ss_slots + k];
+          if (rowss != nullptr) {   // fused RMSNorm: F.normalize(x, dim=-1) of the GEMM input (bs_roformer.py:49)
+            float ssum;
+            if (ss_slots == 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(rowss) + mm);
+              ssum = ((s4.x + s4.y) + s4.z) + s4.w;
+            } else {
+              ssum = 0.f;
+              for (int k = 0; k < ss_slots; ++k) ssum += rowss[(int64_t)mm * ss_slots + k];
+            }
             r = 1.0f / fmaxf(sqrtf(ssum), 1e-12f);
           }
         }
@@ -326,7 +342,15 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
           const int qq = mm / rm_F;
           orow4[it] = (int64_t)(2 * qq + rm_dt) * (2 * rm_F) + 2 * (mm - qq * rm_F) + rm_df;
         }
-        pos4[it] = rot_cols > 0 ? (mm / ep.pos_div) % ep.pos_mod : 0;
+        int pp = 0;
+        if (rot_cols > 0) {
+          int rr = pos_r + it * 8, qa = pos_q;
+          if (ep.pos_div == 1) { qa += rr; rr = 0; }
+          while (rr >= ep.pos_div) { rr -= ep.pos_div; ++qa; }
+          while (qa >= ep.pos_mod) qa -= ep.pos_mod;
+          pp = qa;
+        }
+        pos4[it] = pp;
       }
       const bool c_vec = Cp == nullptr || ((ldc & 3) == 0 && (c_col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
       const bool p_vec = Pp == nullptr || ((ldp & 3) == 0 && (p_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(Pp) & 7) == 0);
