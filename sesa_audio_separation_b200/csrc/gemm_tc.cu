@@ -1,16 +1,20 @@
 // Grouped GEMM on the Blackwell 5th-generation tensor cores:  C = epi( A[M,K] . W[N,K]^T ).
 //
-// Serves the nn.Linear call sites of the RoFormer forward (bs_roformer.py:63,67 FeedForward; :99,104
-// to_qkv / to_out; :237 BandSplit; :264 MaskEstimator MLP).  Design (B200-first, not a translation of
-// anything in the reference, which only calls cuBLAS through PyTorch):
-//   * persistent CTAs (one per SM) walk a tile list that spans all problems of a grouped launch;
-//   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled 64-wide K slabs, mbarrier pipeline),
-//     warp 1 = single-thread tcgen05.mma issuer, accumulators in TMEM (two BN-column buffers, so the
-//     epilogue of tile i overlaps the main loop of tile i+1), warps 2-5 = epilogue (tcgen05.ld);
+// Serves the nn.Linear call sites of the RoFormer forward (bs_roformer.py:63,67 FeedForward; :99,104 to_qkv / to_out;
+// :264 MaskEstimator MLP) and, through the implicit-GEMM mode, the convolutions and Linears of MDX23C
+// (mdx23c_tfc_tdf_v3.py:74-138).  Design (B200-first, not a translation of anything in the reference, which only
+// calls cuBLAS / cuDNN through PyTorch):
+//   * persistent CTAs walk a tile list that spans all problems of a grouped launch (per-problem TMA maps in HBM);
+//   * CG = 2 (default): a cluster of two CTAs owns a 256 x 256 tile with tcgen05.mma.cta_group::2 — each CTA stages its
+//     own 128 rows of A and half of the W tile, the leader issues the MMAs, commits are multicast to both CTAs;
+//   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled 64-wide K slabs, mbarrier ring), warp 1 =
+//     single-thread tcgen05.mma issuer with fp32 accumulators in TMEM (two BN-column buffers: the epilogue of tile i
+//     overlaps the main loop of tile i+1), warps 2-9 = epilogue (tcgen05.ld -> smem transpose -> coalesced phase);
 //   * fp32 parity on bf16 tensor cores: operands are bf16 hi/lo planes and each K slab issues
 //     Ahi.Whi + Ahi.Wlo + Alo.Whi into the same fp32 TMEM accumulator (NSPLIT = 3); NSPLIT = 1 is plain bf16;
-//   * the epilogue fuses row scale (RMSNorm), bias, GELU/tanh/sigmoid, rotary embedding, GLU, residual add,
-//     and writes fp32 and/or the bf16 planes the next tensor-core op consumes.
+//   * the epilogue fuses row scale (RMSNorm, from per-row sum-of-squares slots), bias, GELU/tanh/sigmoid, rotary
+//     embedding, GLU, residual add, the next layer's row sums of squares, and writes fp32 and/or the bf16 planes the
+//     next tensor-core op consumes; convolution taps are shifted TMA boxes, ConvTranspose scatters rows (row_map).
 #include <string.h>
 
 #include "common.cuh"
