@@ -24,6 +24,7 @@ extern "C" {
 #endif
 
 #define SESA_B200_ABI_VERSION 2
+#define SESA_TC_SS_SLOTS_PER_BLOCK 2 /* row-sum-of-squares slots a GEMM writes per column block (one per epilogue warp of a TMEM quadrant) */
 
 enum { SESA_ACT_NONE = 0, SESA_ACT_GELU = 1, SESA_ACT_TANH = 2, SESA_ACT_SIGMOID = 3 };
 
@@ -124,7 +125,7 @@ typedef struct sesa_tc_problem {
    * (mdx23c_tfc_tdf_v3.py:80): row = (2*(m / rm_F) + rm_dt) * 2*rm_F + 2*(m % rm_F) + rm_df. */
   int32_t row_map, rm_F, rm_dt, rm_df;
   /* Fused RMSNorm bookkeeping (bs_roformer.py:43-50 applied to the residual stream without a separate pass):
-   * ss_out (producer, optional): ss_out[row * 2*ceil(N/block_n) + slot] receives this launch's per-row partial sums of
+   * ss_out (producer, optional): ss_out[row * SESA_TC_SS_SLOTS_PER_BLOCK*ceil(N/block_n) + slot] receives this launch's per-row partial sums of
    *   squares of the stored values, one slot per (column block, column half) — deterministic, no atomics;
    * rowss (consumer, optional): acc[m,:] *= 1 / max(sqrt(sum_k rowss[m*ss_slots + k]), 1e-12). */
   const float* rowss;

@@ -26,8 +26,10 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;            // one 128-byte swizzle row of bf16
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;      // two per TMEM lane quadrant, each owning half of the tile's columns
-constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_WARPS = 8;      // two per TMEM lane quadrant, each owning half of the tile's columns (16 warps at
+                                  // <= 112 registers spill ~400 bytes per thread and run 40 % slower: measured, round 1)
+constexpr int NCH = EPI_WARPS / 4; // column slices per tile (one per epilogue warp of a quadrant)
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int EPI_COLS = 16;      // accumulator columns per epilogue step
 constexpr int EPI_STAGE_BYTES = 32 * EPI_COLS * 4;  // per-warp transpose buffer (2 KB)
 constexpr int MAX_GROUPS = 1024;
@@ -280,7 +282,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     const int ew = warp - 2;
     const int q = warp & 3;          // TMEM lane quadrant this warp may access
     const int ch = ew >> 2;          // which half of the tile's columns
-    constexpr int HALF = BN / 2;
+    constexpr int HALF = BN / NCH;   // columns per epilogue warp
     const uint32_t stage = tc::smem_u32(smem + C::EPI_OFF + ew * EPI_STAGE_BYTES);   // byte address in shared space
     constexpr bool kGeneric = FLAVOR == F_GENERIC;
     const bool use_glu = FLAVOR == F_GLU || (kGeneric && ep.glu);
@@ -333,6 +335,10 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             if (ss_slots == 4) {
               const float4 s4 = __ldg(reinterpret_cast<const float4*>(rowss) + mm);
               ssum = ((s4.x + s4.y) + s4.z) + s4.w;
+            } else if (ss_slots == 8) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(rowss) + 2 * (int64_t)mm);
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(rowss) + 2 * (int64_t)mm + 1);
+              ssum = ((((((s4.x + s4.y) + s4.z) + s4.w) + t4.x) + t4.y) + t4.z) + t4.w;
             } else {
               ssum = 0.f;
               for (int k = 0; k < ss_slots; ++k) ssum += rowss[(int64_t)mm * ss_slots + k];
@@ -559,13 +565,13 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
         if (CG == 2) tc::mbar_arrive_leader(&tmem_empty[as]); else tc::mbar_arrive(&tmem_empty[as]);
       }
       if (ss_out != nullptr) {   // this warp's slot of the row sums of squares (4 lanes per row)
-        const int slots = 2 * g->n_blocks;
+        const int slots = NCH * g->n_blocks;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float v = ssq[it];
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
-          if (c4 == 0 && ok4[it]) ss_out[orow4[it] * slots + 2 * nb + ch] = v;
+          if (c4 == 0 && ok4[it]) ss_out[orow4[it] * slots + NCH * nb + ch] = v;
         }
       }
       if (++as == 2) { as = 0; aph ^= 1; }

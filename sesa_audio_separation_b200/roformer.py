@@ -348,7 +348,7 @@ class _RoformerBase(KernelModule):
         x = ws['x']
         # per-row partial sums of squares of the residual stream, written by the residual GEMM epilogues (one slot per
         # column block and half) and consumed as the fused RMSNorm row scale of the next GEMM
-        slots = 2 * ((D + 255) // 256)
+        slots = tc.SS_SLOTS_PER_BLOCK * ((D + 255) // 256)
         ws['ss_slots'] = slots
         ws['ss'] = torch.zeros(M, slots, device=dev, dtype=torch.float32)
         ss_ptr = ws['ss'].data_ptr()

@@ -56,6 +56,7 @@ def prep_rows(x, rows, dim, ldx, planes, normalize, gate_w=None, gate_b=None, ga
 # CTA pairs (tcgen05 cta_group::2, 256 x 256 pair tiles) are the default for the 256-wide tile: they halve the W-tile
 # traffic and reach 1.2-1.55 PFLOP/s of issued MMA where single-CTA tiles stall on L2 (profiles/r1_microbench.md)
 DEFAULT_CTA_GROUP = 2
+SS_SLOTS_PER_BLOCK = 2   # SESA_TC_SS_SLOTS_PER_BLOCK of include/sesa_b200.h
 
 
 class TcGemmTable:
