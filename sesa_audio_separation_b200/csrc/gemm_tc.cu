@@ -370,10 +370,9 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       tc::mbar_wait(&tmem_full[as], aph);
       tc::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + ch * HALF;
-      // software-pipelined per-step constants: the bias quad of this lane's 4 columns and, for rotary columns, the
-      // (cos, sin) quads of its 4 rows are fetched one 16-column step ahead so their latency hides under the current step
+      // software-pipelined per-step constant: the bias quad of this lane's 4 columns is fetched one 16-column step ahead
+      // so that its latency hides under the current step
       float4 b4_next = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 cs_next[4];
       auto load_step_constants = [&](int cstep) {
         const int nn = n_half + cstep * EPI_COLS;
         const int cb = nn + c4 * 4;
@@ -388,12 +387,6 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               if (cb + 3 < N) b4_next.w = bias[cb + 3];
             }
           }
-          if (nn < rot_cols) {
-            const int rd = (cb % ep.rot_dim) >> 1;
-#pragma unroll
-            for (int it = 0; it < 4; ++it)
-              cs_next[it] = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rd) >> 1));
-          }
         }
       };
       load_step_constants(0);
@@ -402,6 +395,16 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
         const int n = n_half + c * EPI_COLS;
         if (n >= N) break;  // warp-uniform
         const int colb = n + c4 * 4;
+        // rotary (cos, sin) quads of this lane's 4 rows: issued before the TMEM load / transpose so that their latency
+        // hides under phase A (kept out of the one-step-ahead prefetch to save 16 registers)
+        const bool do_rot = n < rot_cols;
+        float4 cs4[4];
+        if (do_rot) {
+          const int rd = (colb % ep.rot_dim) >> 1;
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            cs4[it] = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rd) >> 1));
+        }
         // ---- phase A
         {
           float v[EPI_COLS];
@@ -415,10 +418,6 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
         // per-lane constants of this step (bias quad, rotary quads) were loaded one step ahead; fetch the next step's now
         const bool interior = vec_ok && n + EPI_COLS <= N;   // warp-uniform: no ragged right edge in this step
         const float4 b4 = b4_next;
-        const bool do_rot = n < rot_cols;
-        float4 cs4[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) cs4[it] = cs_next[it];
         load_step_constants(c + 1);
         float4 res[4];
         if (ep.residual && interior) {   // issue the residual reads before the shared-memory round trip completes
