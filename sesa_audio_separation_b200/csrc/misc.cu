@@ -47,6 +47,35 @@ extern "C" int sesa_pad_reflect(const float* src, float* dst, int channels, int6
   return SESA_OK;
 }
 
+// 128-bit form of frame_chunks_kernel for 4-aligned geometry (chunk starts, lengths' interior and L multiples of 4).
+__global__ void __launch_bounds__(256) frame_chunks_vec4_kernel(const float* __restrict__ mix, int64_t mix_len, int channels,
+                                                                const int64_t* __restrict__ starts,
+                                                                const int64_t* __restrict__ lens,
+                                                                const int32_t* __restrict__ modes, int64_t L,
+                                                                float* __restrict__ chunks) {
+  const int k = blockIdx.z, c = blockIdx.y;
+  const int64_t s = starts[k], n = lens[k];
+  const int mode = modes[k];
+  const float* src = mix + c * mix_len + s;
+  float* dst = chunks + ((int64_t)k * channels + c) * L;
+  const bool aligned = ((s & 3) == 0) && ((mix_len & 3) == 0);
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < L; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    float4 v;
+    if (aligned && i + 3 < n) {
+      v = *reinterpret_cast<const float4*>(src + i);
+    } else {
+      float e[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t ii = i + j;
+        e[j] = ii < n ? src[ii] : (mode == 1 ? src[2 * (n - 1) - ii] : 0.f);
+      }
+      v = make_float4(e[0], e[1], e[2], e[3]);
+    }
+    *reinterpret_cast<float4*>(dst + i) = v;
+  }
+}
+
 __global__ void frame_chunks_kernel(const float* __restrict__ mix, int64_t mix_len, int channels,
                                     const int64_t* __restrict__ starts, const int64_t* __restrict__ lens,
                                     const int32_t* __restrict__ modes, int64_t L, float* __restrict__ chunks) {
@@ -68,6 +97,13 @@ extern "C" int sesa_frame_chunks(const float* mix, int64_t mix_len, int channels
                                  float* chunks, void* stream) {
   if (n_chunks == 0) return SESA_OK;
   SESA_CHECK_ARG(n_chunks <= 65535, "sesa_frame_chunks: too many chunks in one call (%d)", n_chunks);
+  if ((chunk_size & 3) == 0 && (reinterpret_cast<uintptr_t>(mix) & 15) == 0 && (reinterpret_cast<uintptr_t>(chunks) & 15) == 0) {
+    dim3 gridv((unsigned)min((int64_t)128, ceil_div64(chunk_size, 1024)), channels, n_chunks);
+    frame_chunks_vec4_kernel<<<gridv, 256, 0, (cudaStream_t)stream>>>(mix, mix_len, channels, starts, lens, modes,
+                                                                     chunk_size, chunks);
+    SESA_LAUNCH_CHECK();
+    return SESA_OK;
+  }
   dim3 grid((unsigned)min((int64_t)256, ceil_div64(chunk_size, 256)), channels, n_chunks);
   frame_chunks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mix, mix_len, channels, starts, lens, modes,
                                                               chunk_size, chunks);
@@ -123,6 +159,87 @@ __global__ void overlap_add_kernel(const float* __restrict__ y, const int64_t* _
   }
 }
 
+// Vectorised form of overlap_add_kernel: one thread finishes 4 consecutive output samples with 128-bit loads of the
+// chunk outputs and of the window (same ascending-chunk accumulation per sample, separate multiply and add, so the
+// result and the counter stay bit-identical to the scalar kernel).  Requires step, L, crop and the chunk starts to be
+// multiples of 4 and 16-byte aligned rows (checked by the host entry); ragged chunk ends fall back to per-sample code.
+__global__ void __launch_bounds__(256) overlap_add_vec4_kernel(
+    const float* __restrict__ y, const int64_t* __restrict__ starts, const int64_t* __restrict__ lens,
+    const int32_t* __restrict__ kinds, int n_chunks, int64_t step, int64_t L, int fade, const float* __restrict__ window,
+    int nc, int64_t padded_len, int64_t crop, int64_t out_len, float* __restrict__ result, float* __restrict__ counter) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t total = counter ? padded_len : out_len;
+  if (i4 >= total) return;
+  const int64_t p = counter ? i4 : i4 + crop;   // padded coordinate of the first of the 4 samples (multiple of 4)
+  int64_t k_hi = (p + 3) / step;
+  if (k_hi > n_chunks - 1) k_hi = n_chunks - 1;
+  int64_t k_lo = (p - L + step) / step;
+  if (p - L + 1 <= 0) k_lo = 0;
+  float cnt[4] = {0.f, 0.f, 0.f, 0.f};
+  float wq[8][4];   // window values of the up to 8 covering chunks k_lo + j (statically indexed: stays in registers)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int64_t k = k_lo + j;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wq[j][e] = -1.0f;   // sentinel: sample not covered by this chunk
+    if (k <= k_hi) {
+      const int64_t o = p - starts[k];
+      const int64_t n = lens[k];
+      const int kind = kinds[k];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t oe = o + e;
+        if (oe >= 0 && oe < n) {
+          const float w = demix_window(window, oe, L, fade, kind);
+          wq[j][e] = w;
+          cnt[e] = __fadd_rn(cnt[e], w);
+        }
+      }
+    }
+  }
+  if (counter) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (p + e < padded_len) counter[p + e] = cnt[e];
+  }
+  const int64_t io = p - crop;
+  if (io + 3 < 0 || io >= out_len) return;
+  for (int sc = 0; sc < nc; ++sc) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t k = k_lo + j;
+      if (k > k_hi) continue;
+      const int64_t o = p - starts[k];
+      const float* yp = y + ((int64_t)k * nc + sc) * L + o;
+      if (o >= 0 && o + 3 < lens[k]) {
+        const float4 v = *reinterpret_cast<const float4*>(yp);
+        acc[0] = __fadd_rn(acc[0], __fmul_rn(v.x, wq[j][0]));
+        acc[1] = __fadd_rn(acc[1], __fmul_rn(v.y, wq[j][1]));
+        acc[2] = __fadd_rn(acc[2], __fmul_rn(v.z, wq[j][2]));
+        acc[3] = __fadd_rn(acc[3], __fmul_rn(v.w, wq[j][3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (wq[j][e] >= 0.f) acc[e] = __fadd_rn(acc[e], __fmul_rn(yp[e], wq[j][e]));
+      }
+    }
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      r[e] = acc[e] / cnt[e];
+      if (r[e] != r[e]) r[e] = 0.f;
+    }
+    float* rp = result + (int64_t)sc * out_len + io;
+    if (io >= 0 && io + 3 < out_len) *reinterpret_cast<float4*>(rp) = make_float4(r[0], r[1], r[2], r[3]);
+    else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (io + e >= 0 && io + e < out_len) rp[e] = r[e];
+    }
+  }
+}
+
 extern "C" int sesa_overlap_add(const float* chunk_out, const int64_t* starts, const int64_t* lens,
                                 const int32_t* kinds, int n_chunks, int64_t step, int64_t chunk_size, int fade,
                                 const float* window, int nstems, int channels, int64_t padded_len,
@@ -131,6 +248,16 @@ extern "C" int sesa_overlap_add(const float* chunk_out, const int64_t* starts, c
   SESA_CHECK_ARG(crop >= 0 && crop + out_len <= padded_len, "sesa_overlap_add: crop range outside the padded mix");
   const int64_t total = counter ? padded_len : out_len;
   if (total == 0) return SESA_OK;
+  const bool vec = (step & 3) == 0 && (chunk_size & 3) == 0 && (crop & 3) == 0 && (out_len & 3) == 0 &&
+                   chunk_size <= 8 * step && (reinterpret_cast<uintptr_t>(chunk_out) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(result) & 15) == 0;   // chunk starts are multiples of step
+  if (vec) {
+    overlap_add_vec4_kernel<<<(unsigned)ceil_div64(ceil_div64(total, 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        chunk_out, starts, lens, kinds, n_chunks, step, chunk_size, fade, window, nstems * channels, padded_len, crop,
+        out_len, result, counter);
+    SESA_LAUNCH_CHECK();
+    return SESA_OK;
+  }
   overlap_add_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
       chunk_out, starts, lens, kinds, n_chunks, step, chunk_size, fade, window, nstems, channels, padded_len,
       crop, out_len, result, counter);
