@@ -186,16 +186,25 @@ def denormalize_audio(audio, norm_params):
     return audio * norm_params["std"] + norm_params["mean"]
 
 
+# Test-time augmentations of utils.py:241-292 as (forward transform, inverse transform) pairs: channel swap and
+# polarity inversion.  The result is the plain mean of the un-augmented estimate and the inverted augmented estimates,
+# accumulated in the reference's order (+ swap, - polarity, / 3) so the arithmetic is identical.
+_TTA_VARIANTS = (
+    (lambda m: m[::-1].copy(), lambda w: w[::-1].copy(), +1.0),
+    (lambda m: -1.0 * m.copy(), lambda w: w, -1.0),
+)
+
+
 def apply_tta(config, model, mix, waveforms_orig, device, model_type):
-    """utils.py:241-292."""
-    track_proc_list = [mix[::-1].copy(), -1.0 * mix.copy()]
-    for i, augmented_mix in enumerate(track_proc_list):
-        waveforms = demix(config, model, augmented_mix, device, model_type=model_type)
-        for el in waveforms:
-            if i == 0:
-                waveforms_orig[el] += waveforms[el][::-1].copy()
+    """Drop-in for utils.apply_tta: averages ``waveforms_orig`` with the estimates of the augmented mixes (in place)."""
+    for forward, inverse, sign in _TTA_VARIANTS:
+        estimates = demix(config, model, forward(mix), device, model_type=model_type)
+        for name, wave in estimates.items():
+            if sign > 0:
+                waveforms_orig[name] += inverse(wave)
             else:
-                waveforms_orig[el] -= waveforms[el]
-    for el in waveforms_orig:
-        waveforms_orig[el] /= len(track_proc_list) + 1
+                waveforms_orig[name] -= inverse(wave)
+    scale = len(_TTA_VARIANTS) + 1
+    for name in waveforms_orig:
+        waveforms_orig[name] /= scale
     return waveforms_orig

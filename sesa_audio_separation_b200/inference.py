@@ -72,6 +72,27 @@ def load_checkpoint_into(model, path, device):
     model.load_state_dict(checkpoint, strict=False)
 
 
+def _phase_remix(config, model, args, device, mix_orig, estimates, instruments):
+    """"DemudPhaseRemix" instrumental (inference_pytorch.py:233-250): separate a second time from a mix in which the
+    lead stem's polarity is flipped (mix -/+ 2*lead) and recombine, so that lead residue cancels instead of adding."""
+    lead = 'vocals' if 'vocals' in instruments else instruments[0]
+    has_instrumental = 'instrumental' in instruments or 'Instrumental' in instruments
+
+    def second_pass(flipped_mix, tta_base):
+        est = demix(config, model, flipped_mix, device, model_type=args.model_type)
+        if args.use_tta:
+            est = apply_tta(config, model, flipped_mix, tta_base if tta_base is not None else est, device, args.model_type)
+        return est
+
+    if not has_instrumental:
+        flipped = mix_orig - 2 * estimates[lead]
+        return mix_orig + second_pass(flipped, None)[lead]
+    flipped = 2 * estimates[lead] - mix_orig
+    kept = flipped.copy()
+    # (the reference passes the FIRST pass's estimates as the TTA accumulator in this branch, :247)
+    return mix_orig + kept - second_pass(flipped, estimates)[lead]
+
+
 def run_folder(backend, args, config, device, model=None):
     start_time = time.time()
     mixture_paths = sorted(glob.glob(os.path.join(args.input_folder, '*.*')))
@@ -99,21 +120,9 @@ def run_folder(backend, args, config, device, model=None):
         if args.use_tta and model is not None:
             waveforms_orig = apply_tta(config, model, mix, waveforms_orig, device, args.model_type)
         if args.demud_phaseremix_inst and model is not None:
-            instr = 'vocals' if 'vocals' in instruments else instruments[0]
             instruments.append('instrumental_phaseremix')
-            if 'instrumental' not in instruments and 'Instrumental' not in instruments:
-                mix_modified = mix_orig - 2 * waveforms_orig[instr]
-                waveforms_modified = demix(config, model, mix_modified, device, model_type=args.model_type)
-                if args.use_tta:
-                    waveforms_modified = apply_tta(config, model, mix_modified, waveforms_modified, device, args.model_type)
-                waveforms_orig['instrumental_phaseremix'] = mix_orig + waveforms_modified[instr]
-            else:
-                mix_modified = 2 * waveforms_orig[instr] - mix_orig
-                mix_modified_ = mix_modified.copy()
-                waveforms_modified = demix(config, model, mix_modified, device, model_type=args.model_type)
-                if args.use_tta:
-                    waveforms_modified = apply_tta(config, model, mix_modified, waveforms_orig, device, args.model_type)
-                waveforms_orig['instrumental_phaseremix'] = mix_orig + mix_modified_ - waveforms_modified[instr]
+            waveforms_orig['instrumental_phaseremix'] = _phase_remix(
+                config, model, args, device, mix_orig, waveforms_orig, instruments)
         if args.extract_instrumental:
             instr = 'vocals' if 'vocals' in instruments else instruments[0]
             waveforms_orig['instrumental'] = mix_orig - waveforms_orig[instr]

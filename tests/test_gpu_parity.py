@@ -267,3 +267,23 @@ def test_demix_mdx23c_vs_oracle():
         print('demix mdx23c', k, 'max_rel', max_rel(ref[i], res[k]), 'snr', snr_db(ref[i], res[k]))
         assert max_rel(ref[i], res[k]) <= FP32_MAX_REL
         assert snr_db(ref[i], res[k]) >= FP32_SNR_DB
+
+
+def test_apply_tta_matches_reference_formula():
+    """utils.apply_tta (utils.py:241-292): (orig + swap(demix(swap(mix))) - demix(-mix)) / 3 in the reference's order."""
+    import sesa_audio_separation_b200 as sesa
+    case = CASES['bs_small']
+    model, _ = build(case)
+    L = 441 * 40
+    cfg = sesa.ConfigDict(dict(audio=dict(chunk_size=L), inference=dict(num_overlap=2, batch_size=1),
+                               training=dict(instruments=['vocals', 'other'], target_instrument='vocals')))
+    mix = synth_mix(L * 2 + 100, 2, seed=61)
+    base = sesa.demix(cfg, model, mix, 'cuda', 'bs_roformer')
+    a = sesa.demix(cfg, model, mix[::-1].copy(), 'cuda', 'bs_roformer')['vocals']
+    b = sesa.demix(cfg, model, -1.0 * mix.copy(), 'cuda', 'bs_roformer')['vocals']
+    want = base['vocals'].copy()
+    want += a[::-1].copy()
+    want -= b
+    want /= 3
+    got = sesa.apply_tta(cfg, model, mix, {k: v.copy() for k, v in base.items()}, 'cuda', 'bs_roformer')
+    assert np.array_equal(got['vocals'], want)
