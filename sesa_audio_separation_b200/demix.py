@@ -54,7 +54,9 @@ class DemixEngine:
         self.num_overlap = int(config.inference.num_overlap)
         self.batch_size = int(config.inference.batch_size)
         self.instruments = list(prefer_target_instrument(config))
-        self.engine_batch = int(engine_batch or max(1, min(8, self.batch_size * 2)))
+        # chunks per launch group: a throughput knob only (results are batch-invariant); 4 fills the 148 SMs' tile
+        # waves of every GEMM at the BASELINE model sizes and keeps the workspace under 40 GB
+        self.engine_batch = int(engine_batch or 4)
         self.world, self.rank, self.group = world, rank, group
         self.progress = progress
 

@@ -287,3 +287,28 @@ def test_apply_tta_matches_reference_formula():
     want /= 3
     got = sesa.apply_tta(cfg, model, mix, {k: v.copy() for k, v in base.items()}, 'cuda', 'bs_roformer')
     assert np.array_equal(got['vocals'], want)
+
+
+def test_hop512_config_and_odd_lengths_vs_oracle():
+    """The other RoFormer geometry named by the north star (hop 512, ZFTurbo-style generic config) through demix(), with a
+    mix length that leaves ragged tail chunks; checked against the oracle's demix + forward on the CPU."""
+    import sesa_audio_separation_b200 as sesa
+    from oracle import roformer as orof
+    cfg = dict(dim=64, depth=1, stereo=True, num_stems=1, time_transformer_depth=1, freq_transformer_depth=1, dim_head=64,
+               heads=2, stft_n_fft=2048, stft_hop_length=512, stft_win_length=2048, mask_estimator_depth=2,
+               mlp_expansion_factor=2)
+    model = sesa.BSRoformer(**cfg)
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=71)
+    model.load_state_dict(sd)
+    model.eval().to('cuda')
+    L = 512 * 24
+    config = sesa.ConfigDict(dict(audio=dict(chunk_size=L), inference=dict(num_overlap=4, batch_size=2),
+                                  training=dict(instruments=['vocals', 'other'], target_instrument='vocals')))
+    for length in (L * 3 + 1357, L // 3, 2 * L):
+        mix = synth_mix(length, 2, seed=72 + length % 7)
+        got = sesa.demix(config, model, mix, 'cuda', 'bs_roformer')['vocals']
+        with torch.inference_mode():
+            ref = odemix.demix(mix, lambda a: orof.bs_roformer_forward(sd, cfg, a), L, 4, 2, 1)[0]
+        print('hop512 length', length, 'max_rel', max_rel(ref, got), 'snr', snr_db(ref, got))
+        assert got.shape == ref.shape
+        assert max_rel(ref, got) <= FP32_MAX_REL and snr_db(ref, got) >= FP32_SNR_DB
