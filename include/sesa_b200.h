@@ -133,7 +133,7 @@ typedef struct sesa_tc_problem {
   int32_t ss_slots;
   int32_t p_cols;   /* planes P are written for columns n < p_cols (0 = all columns) */
   int32_t c_col0;   /* C is written for columns n >= c_col0, at column n - c_col0 (to_gates logits next to to_qkv) */
-  int32_t _pad2;
+  int32_t ss_ld;    /* floats between consecutive rows of ss_out (0 = SESA_TC_SS_SLOTS_PER_BLOCK * ceil(N/block_n)) */
 } sesa_tc_problem;
 
 /* Bytes of the device-side group table for n_groups problems. */
@@ -170,6 +170,10 @@ int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t plane_stride, 
 int sesa_prep_rows(const float* x, int64_t ldx, int64_t rows, int dim, int normalize, void* planes, int64_t ldp,
                    int64_t p_plane, int out_planes, const float* gate_w, const float* gate_b, int n_gates,
                    float* gates, int64_t ldg, float* rowinv, int ss_slots, void* stream);
+/* BandSplit prologue (bs_roformer.py:241-249): planes[p][r][plane_offs[b] + i] = split(feat[r][offs[b] + i] / max(||feat[r][offs[b]:offs[b+1]]||, 1e-12)),
+ * zero padded up to plane_offs[b+1] (multiples of 8 so that every band is a 16-byte aligned TMA operand). */
+int sesa_band_prep(const float* feat, int64_t ld_feat, int64_t rows, int n_bands, const int32_t* offs,
+                   const int32_t* plane_offs, void* planes, int64_t ldp, int64_t p_plane, int out_planes, void* stream);
 /* bf16 hi/lo planes of a weight matrix w[rows][cols] -> planes[2][rows][ldp] (zero padded to ldp). */
 int sesa_split_weight(const float* w, int64_t rows, int64_t cols, void* planes, int64_t ldp, void* stream);
 

@@ -41,7 +41,7 @@ TC_PROBLEM_DTYPE = np.dtype([('A', '<u8'), ('W', '<u8'), ('bias', '<u8'), ('rows
                              ('conv_dt', '<i4', (9,)), ('conv_df', '<i4', (9,)),
                              ('row_map', '<i4'), ('rm_F', '<i4'), ('rm_dt', '<i4'), ('rm_df', '<i4'),
                              ('rowss', '<u8'), ('ss_out', '<u8'), ('ss_slots', '<i4'), ('p_cols', '<i4'),
-                             ('c_col0', '<i4'), ('_pad2', '<i4')])
+                             ('c_col0', '<i4'), ('ss_ld', '<i4')])
 assert TC_PROBLEM_DTYPE.itemsize == 272
 
 _SIGS = {
@@ -65,6 +65,8 @@ _SIGS = {
                                   c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     'sesa_prep_rows': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_int64, c_int,
                                c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    'sesa_band_prep': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                               c_void_p]),
     'sesa_split_weight': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     'sesa_rmsnorm': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     'sesa_add_inplace': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -118,7 +120,7 @@ def check(status):
 # ---- launch accounting / per-kernel-class timing (bench.py, profiling); off by default
 LAUNCHES = 0
 _profile = None   # dict: class -> [ (start_event, end_event), ... ] when enabled
-_CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_instnorm_stats': 'norm', 'sesa_norm_act_split': 'norm', 'sesa_transpose_add': 'norm', 'sesa_attention_simt': 'attention',
+_CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_band_prep': 'prep_rows', 'sesa_instnorm_stats': 'norm', 'sesa_norm_act_split': 'norm', 'sesa_transpose_add': 'norm', 'sesa_attention_simt': 'attention',
           'sesa_attention_tc': 'attention', 'sesa_stft': 'stft', 'sesa_mask_istft': 'mask_istft',
           'sesa_overlap_add': 'overlap_add', 'sesa_overlap_add_range': 'overlap_add', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}
 

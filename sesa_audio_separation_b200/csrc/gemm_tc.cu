@@ -54,7 +54,7 @@ struct alignas(128) TcGroup {
   int32_t ss_slots;     // slots per row in rowss
   int32_t p_cols;       // planes are written for columns < p_cols (0 = all)
   int32_t c_col0;       // C is written for columns >= c_col0, at column n - c_col0
-  int32_t _r2;
+  int32_t ss_ld;        // floats between consecutive rows of ss_out (>= slots; lets band-sliced launches interleave)
 };
 static_assert(sizeof(TcGroup) % 128 == 0, "table entries must keep the tensor maps 128-byte aligned");
 
@@ -564,13 +564,13 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
         if (CG == 2) tc::mbar_arrive_leader(&tmem_empty[as]); else tc::mbar_arrive(&tmem_empty[as]);
       }
       if (ss_out != nullptr) {   // this warp's slot of the row sums of squares (4 lanes per row)
-        const int slots = NCH * g->n_blocks;
+        const int ss_ld = g->ss_ld;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           float v = ssq[it];
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
-          if (c4 == 0 && ok4[it]) ss_out[orow4[it] * slots + NCH * nb + ch] = v;
+          if (c4 == 0 && ok4[it]) ss_out[orow4[it] * ss_ld + NCH * nb + ch] = v;
         }
       }
       if (++as == 2) { as = 0; aph ^= 1; }
@@ -756,6 +756,7 @@ extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int b
     g.ss_slots = p.ss_slots;
     g.p_cols = p.p_cols;
     g.c_col0 = p.c_col0;
+    g.ss_ld = p.ss_ld > 0 ? p.ss_ld : NCH * ((p.N + block_n - 1) / block_n);
     SESA_CHECK_ARG(p.rowss == nullptr || (p.ss_slots > 0 && p.ss_slots <= 16), "sesa_gemm_tc_build: problem %d: bad ss_slots", i);
     SESA_CHECK_ARG(p.ss_out == nullptr || (p.C == nullptr || ((p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0)),
                    "sesa_gemm_tc_build: problem %d: ss_out needs 16-byte aligned fp32 output rows", i);
@@ -885,6 +886,47 @@ extern "C" int sesa_prep_rows(const float* x, int64_t ldx, int64_t rows, int dim
   prep_rows_kernel<<<(unsigned)ceil_div64(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
       x, ldx, rows, dim, normalize, reinterpret_cast<__nv_bfloat16*>(planes), ldp, p_plane, out_planes, gate_w, gate_b,
       n_gates, gates, ldg, rowinv, ss_slots);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+// BandSplit prologue (bs_roformer.py:241-249; Mel :250-258): per (row, band) L2-normalise the band's slice of the feature
+// row (F.normalize of RMSNorm; gamma*sqrt(dim_in) is folded into the band's weight) and write it as bf16 hi/lo planes at
+// the band's 16-byte aligned plane column — the A operand of the grouped tensor-core GEMM.  One warp per (row, band).
+__global__ void __launch_bounds__(256) band_prep_kernel(const float* __restrict__ feat, int64_t ld_feat, int64_t rows, int nb,
+                                                        const int32_t* __restrict__ offs, const int32_t* __restrict__ poffs,
+                                                        __nv_bfloat16* __restrict__ planes, int64_t ldp, int64_t p_plane,
+                                                        int out_planes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= rows * nb) return;
+  const int64_t r = w / nb;
+  const int b = (int)(w - r * nb);
+  const int c0 = offs[b], n = offs[b + 1] - c0;
+  const int p0 = poffs[b], np = poffs[b + 1] - p0;
+  const float* x = feat + r * ld_feat + c0;
+  float ss = 0.f;
+  for (int i = lane; i < n; i += 32) ss = fmaf(x[i], x[i], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  __nv_bfloat16* pr = planes + r * ldp + p0;
+  for (int i = lane; i < np; i += 32) {
+    __nv_bfloat16 h, l;
+    tc::split_bf16(i < n ? x[i] * inv : 0.f, h, l);
+    pr[i] = h;
+    if (out_planes > 1) pr[i + p_plane] = l;
+  }
+}
+
+extern "C" int sesa_band_prep(const float* feat, int64_t ld_feat, int64_t rows, int n_bands, const int32_t* offs,
+                              const int32_t* plane_offs, void* planes, int64_t ldp, int64_t p_plane, int out_planes,
+                              void* stream) {
+  SESA_CHECK_ARG(n_bands > 0 && (out_planes == 1 || out_planes == 2), "sesa_band_prep: bad arguments");
+  if (rows <= 0) return SESA_OK;
+  const int wpb = 8;
+  band_prep_kernel<<<(unsigned)ceil_div64(rows * n_bands, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      feat, ld_feat, rows, n_bands, offs, plane_offs, reinterpret_cast<__nv_bfloat16*>(planes), ldp, p_plane, out_planes);
   SESA_LAUNCH_CHECK();
   return SESA_OK;
 }

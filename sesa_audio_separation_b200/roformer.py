@@ -215,6 +215,8 @@ class _RoformerBase(KernelModule):
             bs_w.append((P[p + '1.weight'] * (P[p + '0.gamma'] * math.sqrt(din))[None]).contiguous())
             bs_b.append(P[p + '1.bias'].contiguous())
         prep['bs_w'], prep['bs_b'] = bs_w, bs_b
+        if self._tc:
+            prep['bs_wp'] = [tc.split_weight(w) for w in bs_w]
         # mask estimators: final_norm folded into the first Linear (BS), GLU rows interleaved in the last
         fin = (P['final_norm.gamma'] * sD) if self.has_final_norm else None
         me = []
@@ -358,6 +360,21 @@ class _RoformerBase(KernelModule):
                                         bias=bias.data_ptr() if bias is not None else 0,
                                         C=(C.data_ptr(), C.shape[-1]) if C is not None else None,
                                         P=tc.planes_arg(Pl) if Pl is not None else None, **extra)], dev)
+        # BandSplit on the tensor cores: per-band normalised feature planes (bands at 16-byte aligned plane columns) feed
+        # ONE grouped launch whose epilogue also emits the residual stream's planes and row sums of squares
+        offs = np.concatenate([[0], np.cumsum(self.dim_inputs)]).astype(np.int32)
+        poffs = np.concatenate([[0], np.cumsum([tc.round8(d) for d in self.dim_inputs])]).astype(np.int32)
+        ws['bs_offs'] = torch.from_numpy(offs).to(dev)
+        ws['bs_poffs'] = torch.from_numpy(poffs).to(dev)
+        ws['featp'] = tc.alloc_planes(BT, int(poffs[-1]), dev)
+        fp = ws['featp']
+        probs = []
+        for b, din in enumerate(self.dim_inputs):
+            probs.append(dict(A=(fp.data_ptr() + 2 * int(poffs[b]), fp.shape[-1], fp.stride(0)), W=tc.planes_arg(prep['bs_wp'][b]),
+                              M=BT, N=D, K=din, bias=prep['bs_b'][b].data_ptr(), C=(x.data_ptr() + 4 * b * D, nb * D),
+                              P=(ws['xp'].data_ptr() + 2 * b * D, nb * D, ws['xp'].stride(0)),
+                              ss_out=ss_ptr + 4 * b * slots, ss_ld=nb * slots))
+        ws['t_bandsplit'] = tc.TcGemmTable(probs, dev)
         ws['t_layers'] = []
         for pair in prep['layers']:
             gp = []
@@ -472,9 +489,15 @@ class _RoformerBase(KernelModule):
         call('sesa_stft', _ptr(audio), _ptr(ws['spec']), _ptr(prep['window']), _ptr(prep['twiddle']), B, C, L,
              self.n_fft, self.hop, 0, F, st)
         self._gather_features(ws, prep, B, T)
-        self._gemm(ws['g_bandsplit'], _epilogue(rownorm=1))
         if self._tc:
-            self._refresh_planes(ws)
+            nsplit = 3 if self.precision == 'fp32' else 1
+            feat = ws.get('feat', ws['spec'])      # Mel: gathered rows; BS: the spectrogram itself
+            fp = ws['featp']
+            call('sesa_band_prep', _ptr(feat), feat.shape[-1], B * T, self.num_bands, _ptr(ws['bs_offs']), _ptr(ws['bs_poffs']),
+                 _ptr(fp), fp.shape[-1], fp.stride(0), 2 if nsplit == 3 else 1, st)
+            ws['t_bandsplit'].run(_epilogue(), nsplit, 2 if nsplit == 3 else 1)
+        else:
+            self._gemm(ws['g_bandsplit'], _epilogue(rownorm=1))
         for i, (pair, gp) in enumerate(zip(prep['layers'], ws['g_layers'])):
             if self.skip_connection:
                 for j in range(i):

@@ -89,7 +89,7 @@ class TcGemmTable:
                     rec['conv_' + name] = conv[name]
                 rec['conv_dt'][:len(taps)] = [t[0] for t in taps]
                 rec['conv_df'][:len(taps)] = [t[1] for t in taps]
-            for name in ('rowss', 'ss_out', 'ss_slots', 'p_cols', 'c_col0'):
+            for name in ('rowss', 'ss_out', 'ss_slots', 'p_cols', 'c_col0', 'ss_ld'):
                 if p.get(name):
                     rec[name] = p[name]
             rm = p.get('row_map')
