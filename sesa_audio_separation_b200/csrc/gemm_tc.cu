@@ -66,7 +66,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = NP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (196 * 1024) / STAGE_BYTES >= 6 ? 6 : (196 * 1024) / STAGE_BYTES;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int BIAS_OFF = EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;   // per-warp bias slice of the tile (BN / NCH floats)
+  static constexpr int BAR_OFF = BIAS_OFF + BN * 4 * 4;
   static constexpr int TILE_OFF = BAR_OFF + 256;
   static constexpr int SMEM_BYTES = TILE_OFF + MAX_GROUPS * 4 + 1024 /*alignment slack*/;
   static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: power of two
@@ -86,9 +87,39 @@ __device__ __forceinline__ float gelu_fast(float x) {
   r = fmaf(r, u, -5.249617994e-02f);
   r = fmaf(r, u, -4.592081904e-01f);
   r = fmaf(r, u, -1.151105165e+00f);
-  const float e = exp2f(u * r);
+  const float e = tc::ex2_approx(u * r);   // argument in [-60, 0]: no denormal handling needed
   const float ef = copysignf(1.0f - e, x);
   return x * fmaf(0.5f, ef, 0.5f);
+}
+
+// The same polynomial over 16 values, written breadth-first (each Horner step over all 16 before the next) so that the
+// epilogue warps always have independent instructions to issue: two warps per scheduler cannot hide a serial chain.
+__device__ __forceinline__ void gelu_fast16(float4 (&o)[4]) {
+  float x[16], u[16], r[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { x[4 * i] = o[i].x; x[4 * i + 1] = o[i].y; x[4 * i + 2] = o[i].z; x[4 * i + 3] = o[i].w; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) u[i] = fminf(fabsf(x[i]), 6.0f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = fmaf(-2.834913403e-06f, u[i], 3.937759539e-05f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], u[i], -1.861794008e-04f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], u[i], -1.369391393e-04f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], u[i], 7.063424215e-03f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], u[i], -5.249617994e-02f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], u[i], -4.592081904e-01f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], u[i], -1.151105165e+00f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = tc::ex2_approx(u[i] * r[i]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = x[i] * fmaf(0.5f, copysignf(1.0f - r[i], x[i]), 0.5f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
@@ -284,10 +315,12 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     const int ch = ew >> 2;          // which half of the tile's columns
     constexpr int HALF = BN / NCH;   // columns per epilogue warp
     const uint32_t stage = tc::smem_u32(smem + C::EPI_OFF + ew * EPI_STAGE_BYTES);   // byte address in shared space
+    const uint32_t bias_s = tc::smem_u32(smem + C::BIAS_OFF + ew * (BN / NCH) * 4);
     constexpr bool kGeneric = FLAVOR == F_GENERIC;
     const bool use_glu = FLAVOR == F_GLU || (kGeneric && ep.glu);
     const int act = FLAVOR == F_GELU ? SESA_ACT_GELU : FLAVOR == F_TANH ? SESA_ACT_TANH : kGeneric ? ep.act : SESA_ACT_NONE;
     const int rot_cols = (FLAVOR == F_ROT || kGeneric) ? ep.rot_cols : 0;
+    const bool residual = (FLAVOR == F_PLAIN || kGeneric) ? ep.residual != 0 : false;   // only the plain flavour carries the residual stream
     const int c4 = lane & 3;         // phase B: this lane's column quad inside a 16-column step
     const int rb = lane >> 2;        // phase B: row (within each group of 8) handled by this lane
     int as = 0;
@@ -323,29 +356,38 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       }
       const float* __restrict__ rowss = g->rowss;
       const int ss_slots = g->ss_slots;
+      // row scales of the lane's 4 rows: all loads are issued before the first use (rows past M read row M-1's slot)
+      float rsum4[4];
+      {
+        float4 s4[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int64_t mc = min(mm0 + it * 8, M - 1);
+          rsum4[it] = 1.0f;
+          if (g->rowscale != nullptr) rsum4[it] = __ldg(g->rowscale + mc);
+          if (rowss != nullptr) {
+            if (ss_slots == 4) s4[it] = __ldg(reinterpret_cast<const float4*>(rowss) + mc);
+          }
+        }
+        if (rowss != nullptr) {   // fused RMSNorm: F.normalize(x, dim=-1) of the GEMM input (bs_roformer.py:49)
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            float ssum;
+            if (ss_slots == 4) ssum = ((s4[it].x + s4[it].y) + s4[it].z) + s4[it].w;
+            else {
+              const int64_t mc = min(mm0 + it * 8, M - 1);
+              ssum = 0.f;
+              for (int k = 0; k < ss_slots; ++k) ssum += rowss[mc * ss_slots + k];
+            }
+            rsum4[it] = 1.0f / fmaxf(sqrtf(ssum), 1e-12f);
+          }
+        }
+      }
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int mm = mm0 + it * 8;
         ok4[it] = mm < M;
-        float r = 1.0f;
-        if (ok4[it]) {
-          if (g->rowscale != nullptr) r = g->rowscale[mm];
-          if (rowss != nullptr) {   // fused RMSNorm: F.normalize(x, dim=-1) of the GEMM input (bs_roformer.py:49)
-            float ssum;
-            if (ss_slots == 4) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(rowss) + mm);
-              ssum = ((s4.x + s4.y) + s4.z) + s4.w;
-            } else if (ss_slots == 8) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(rowss) + 2 * (int64_t)mm);
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(rowss) + 2 * (int64_t)mm + 1);
-              ssum = ((((((s4.x + s4.y) + s4.z) + s4.w) + t4.x) + t4.y) + t4.z) + t4.w;
-            } else {
-              ssum = 0.f;
-              for (int k = 0; k < ss_slots; ++k) ssum += rowss[(int64_t)mm * ss_slots + k];
-            }
-            r = 1.0f / fmaxf(sqrtf(ssum), 1e-12f);
-          }
-        }
+        const float r = rsum4[it];
         rs4[it] = r;
         if (row_map == 0) orow4[it] = mm;
         else {
@@ -364,39 +406,35 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       }
       const bool c_vec = Cp == nullptr || ((ldc & 3) == 0 && (c_col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(Cp) & 15) == 0);
       const bool p_vec = Pp == nullptr || ((ldp & 3) == 0 && (p_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(Pp) & 7) == 0);
-      const bool b_vec = bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
-      const bool vec_ok = c_vec && p_vec && b_vec;
+      const bool vec_ok = c_vec && p_vec;
+
+      // this warp's bias slice goes to shared memory once per tile (lane -> 4 consecutive columns); the steps read their
+      // quad back with one broadcast ld.shared instead of a global load per step
+      {
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias != nullptr) {
+          const int cb = n_half + lane * 4;
+          if (cb < N) bq.x = __ldg(bias + cb);
+          if (cb + 1 < N) bq.y = __ldg(bias + cb + 1);
+          if (cb + 2 < N) bq.z = __ldg(bias + cb + 2);
+          if (cb + 3 < N) bq.w = __ldg(bias + cb + 3);
+        }
+        if (lane * 4 < HALF) sts128(bias_s + lane * 16, bq);   // ordered before the first read by the in-loop __syncwarp
+      }
 
       tc::mbar_wait(&tmem_full[as], aph);
       tc::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + ch * HALF;
-      // software-pipelined per-step constant: the bias quad of this lane's 4 columns is fetched one 16-column step ahead
-      // so that its latency hides under the current step
-      float4 b4_next = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto load_step_constants = [&](int cstep) {
-        const int nn = n_half + cstep * EPI_COLS;
-        const int cb = nn + c4 * 4;
-        b4_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cstep < HALF / EPI_COLS && nn < N) {
-          if (bias != nullptr) {
-            if (vec_ok && nn + EPI_COLS <= N) b4_next = __ldg(reinterpret_cast<const float4*>(bias + cb));
-            else {
-              if (cb < N) b4_next.x = bias[cb];
-              if (cb + 1 < N) b4_next.y = bias[cb + 1];
-              if (cb + 2 < N) b4_next.z = bias[cb + 2];
-              if (cb + 3 < N) b4_next.w = bias[cb + 3];
-            }
-          }
-        }
-      };
-      load_step_constants(0);
+      // the accumulator columns of step c + 1 are requested from TMEM while step c is being finished
+      float v[EPI_COLS];
+      if (n_half < N) tmem_ld16(t_row, v);
 #pragma unroll 1
       for (int c = 0; c < HALF / EPI_COLS; ++c) {
         const int n = n_half + c * EPI_COLS;
         if (n >= N) break;  // warp-uniform
         const int colb = n + c4 * 4;
-        // rotary (cos, sin) quads of this lane's 4 rows: issued before the TMEM load / transpose so that their latency
-        // hides under phase A (kept out of the one-step-ahead prefetch to save 16 registers)
+        // rotary (cos, sin) quads of this lane's 4 rows: issued before the transpose so that their latency hides under
+        // phase A
         const bool do_rot = n < rot_cols;
         float4 cs4[4];
         if (do_rot) {
@@ -406,27 +444,25 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             cs4[it] = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rd) >> 1));
         }
         // ---- phase A
-        {
-          float v[EPI_COLS];
-          tmem_ld16(t_row + c * EPI_COLS, v);
-          tc::tmem_ld_wait();
+        tc::tmem_ld_wait();
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            sts128(stage + lane * (EPI_COLS * 4) + ((j4 ^ ((lane >> 1) & 3)) << 4),
-                   make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
-        }
-        // per-lane constants of this step (bias quad, rotary quads) were loaded one step ahead; fetch the next step's now
+        for (int j4 = 0; j4 < 4; ++j4)
+          sts128(stage + lane * (EPI_COLS * 4) + ((j4 ^ ((lane >> 1) & 3)) << 4),
+                 make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+        // (the rotary / generic flavours are short of registers: they request the next columns after phase B instead)
+        constexpr bool kEarlyLd = FLAVOR != F_ROT && FLAVOR != F_GENERIC;
+        const bool more = c + 1 < HALF / EPI_COLS && n + EPI_COLS < N;
+        if (kEarlyLd && more) tmem_ld16(t_row + (c + 1) * EPI_COLS, v);
         const bool interior = vec_ok && n + EPI_COLS <= N;   // warp-uniform: no ragged right edge in this step
-        const float4 b4 = b4_next;
-        load_step_constants(c + 1);
         float4 res[4];
-        if (ep.residual && interior) {   // issue the residual reads before the shared-memory round trip completes
+        if (residual && interior) {   // issue the residual reads before the shared-memory round trip completes
 #pragma unroll
           for (int it = 0; it < 4; ++it)
             res[it] = ok4[it] ? *reinterpret_cast<const float4*>(Cp + orow4[it] * ldc + (colb - c_col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
         // ---- phase B
+        const float4 b4 = lds128(bias_s + (c * EPI_COLS + c4 * 4) * 4);
         if (interior && !use_glu) {
           // fast path: straight-line code over the lane's 4 rows (16 independent element chains for the scheduler);
           // only the stores are predicated
@@ -444,11 +480,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             o[it].w = fmaf(o[it].w, rs4[it], b4.w);
           }
           if (act == SESA_ACT_GELU) {
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              o[it].x = gelu_fast(o[it].x); o[it].y = gelu_fast(o[it].y);
-              o[it].z = gelu_fast(o[it].z); o[it].w = gelu_fast(o[it].w);
-            }
+            gelu_fast16(o);
           } else if (act == SESA_ACT_TANH) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
@@ -472,7 +504,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               o[it].w = x4 * cs.z + x3 * cs.w;
             }
           }
-          if (ep.residual) {
+          if (residual) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) { o[it].x += res[it].x; o[it].y += res[it].y; o[it].z += res[it].z; o[it].w += res[it].w; }
           }
@@ -480,7 +512,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
           const bool wp = Pp != nullptr && colb < p_cols;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            ssq[it] += o[it].x * o[it].x + o[it].y * o[it].y + o[it].z * o[it].z + o[it].w * o[it].w;
+            if (ss_out != nullptr) ssq[it] += o[it].x * o[it].x + o[it].y * o[it].y + o[it].z * o[it].z + o[it].w * o[it].w;
             if (wc && ok4[it]) *reinterpret_cast<float4*>(Cp + orow4[it] * ldc + (colb - c_col0)) = o[it];
             if (wp) {
               uint32_t h0, l0, h1, l1;
@@ -543,7 +575,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               float val = ov[e];
               if (Cp != nullptr && colb + e >= c_col0) {
                 float* cp = Cp + orow * ldc + colb + e - c_col0;
-                if (ep.residual) val += *cp;
+                if (residual) val += *cp;
                 *cp = val;
               }
               ssq[it] += val * val;
@@ -556,6 +588,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             }
           }
         }
+        if (!kEarlyLd && more) tmem_ld16(t_row + (c + 1) * EPI_COLS, v);
         __syncwarp();
       }
       tc::tc_fence_before();
