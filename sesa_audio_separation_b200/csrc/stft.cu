@@ -8,6 +8,14 @@
 #include "fft.cuh"
 #include "sesa_b200.h"
 
+// n_fft = 2048 fast paths (stft2048.cu)
+int sesa_launch_stft2048(const float* audio, float* spec, const float* window, const float* twiddle, int n_signals,
+                         int channels, int64_t length, int hop, int T, cudaStream_t stream);
+int sesa_launch_mask_istft2048(const float* spec, const float* mask, const int* inv, const float* cnt, float* out,
+                               const float* window, const float* env, const float* twiddle, int batch, int nstems,
+                               int channels, int hop, int T, int64_t out_len, int mode, int n_gathered,
+                               cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------
 // STFT.  grid = (T, NS) ; one CTA per frame of one signal group (all C<=2 channels of one chunk).
 // layout 0 (RoFormer): spec[(ns*T + t)][f][c][re/im]      ('b t (f s c)', bs_roformer.py:497)
@@ -85,6 +93,8 @@ extern "C" int sesa_stft(const float* audio, float* spec, const float* window, c
   SESA_CHECK_ARG(layout == 0 || layout == 1, "sesa_stft: bad layout %d", layout);
   if (n_signals == 0) return SESA_OK;
   const int T = 1 + (int)(length / hop);
+  if (n_fft == 2048 && layout == 0 && (channels == 1 || (reinterpret_cast<uintptr_t>(spec) & 15) == 0))
+    return sesa_launch_stft2048(audio, spec, window, twiddle, n_signals, channels, length, hop, T, (cudaStream_t)stream);
   const size_t smem = (size_t)2 * n_fft * sizeof(float2);
   SESA_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(T, n_signals);
@@ -222,6 +232,10 @@ extern "C" int sesa_mask_istft(const float* spec, const float* mask, const int* 
   SESA_CHECK_ARG(out_len > 0 && out_len <= (int64_t)hop * (n_frames - 1) + n_fft / 2,
                  "sesa_mask_istft: out_len %lld not covered by %d frames", (long long)out_len, n_frames);
   if (batch == 0 || nstems == 0) return SESA_OK;
+  if (n_fft == 2048 && hop >= 128 && (reinterpret_cast<uintptr_t>(spec) & 15) == 0 &&
+      (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15) == 0))
+    return sesa_launch_mask_istft2048(spec, mask, inv_index, inv_count, out, window, envelope, twiddle, batch, nstems,
+                                      channels, hop, n_frames, out_len, mode, n_gathered, (cudaStream_t)stream);
   int groups_of = 12;  // frames' worth of hops per CTA: (G + n_fft/hop - 1)/G redundant transforms
   while (groups_of > 1 &&
          (size_t)2 * n_fft * sizeof(float2) + (size_t)channels * groups_of * hop * sizeof(float) > 200 * 1024)
