@@ -240,6 +240,94 @@ __global__ void __launch_bounds__(256) overlap_add_vec4_kernel(
   }
 }
 
+// Region form of the vectorised gather (the product path: no counter output).  All samples of one `step`-long region
+// [r * step, (r + 1) * step) of the padded mix are covered by the same chunks, so a block works inside ONE region and the
+// chunk list (starts, lengths, window kinds) is block-uniform: no per-thread 64-bit divisions or schedule loads, only the
+// 128-bit loads of the chunk outputs and of the window.  Arithmetic per sample is unchanged (ascending chunk order, separate
+// multiply and add, divide by the window sum), so the result is bit-identical to the kernels above.
+template <int NK>
+__global__ void __launch_bounds__(256) overlap_add_region_kernel(
+    const float* __restrict__ y, const int64_t* __restrict__ starts, const int64_t* __restrict__ lens,
+    const int32_t* __restrict__ kinds, int n_chunks, int step, int L, int fade, const float* __restrict__ window, int nc,
+    int64_t crop, int64_t out_len, float* __restrict__ result, int blocks_per_region, int span) {
+  const int r = blockIdx.x / blocks_per_region;
+  const int i4 = ((blockIdx.x - r * blocks_per_region) * 256 + threadIdx.x) * 4;   // offset inside the region
+  if (i4 >= step) return;
+  const int64_t p = (int64_t)r * step + i4;
+  const int64_t io = p - crop;
+  if (io < 0 || io >= out_len) return;    // crop and out_len are multiples of 4
+  const int k_hi = min(r, n_chunks - 1);
+  const int k_lo = max(0, r - span + 1);
+  float cnt[4] = {0.f, 0.f, 0.f, 0.f};
+  float wq[NK][4];
+  int oq[NK];          // offset of this thread's first sample inside chunk k_lo + j; -1: chunk absent or not covering
+  bool full[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) {
+    const int k = k_lo + j;
+    oq[j] = -1;
+    full[j] = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wq[j][e] = -1.0f;
+    if (k <= k_hi) {
+      const int64_t o64 = p - starts[k];
+      const int n = (int)lens[k];
+      const int kind = kinds[k];
+      if (o64 >= 0 && o64 < n) {
+        const int o = (int)o64;
+        oq[j] = o;
+        if (o + 3 < n) {
+          full[j] = true;
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(window + o));
+          float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if ((kind == 1 && o + e < fade) || (kind == 2 && o + e >= L - fade)) w[e] = 1.0f;
+            wq[j][e] = w[e];
+            cnt[e] = __fadd_rn(cnt[e], w[e]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (o + e < n) {
+              const float w = demix_window(window, o + e, L, fade, kind);
+              wq[j][e] = w;
+              cnt[e] = __fadd_rn(cnt[e], w);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll 2
+  for (int sc = 0; sc < nc; ++sc) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      if (oq[j] < 0) continue;
+      const float* yp = y + ((int64_t)(k_lo + j) * nc + sc) * L + oq[j];
+      if (full[j]) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(yp));   // streamed once: do not keep in L2
+        acc[0] = __fadd_rn(acc[0], __fmul_rn(v.x, wq[j][0]));
+        acc[1] = __fadd_rn(acc[1], __fmul_rn(v.y, wq[j][1]));
+        acc[2] = __fadd_rn(acc[2], __fmul_rn(v.z, wq[j][2]));
+        acc[3] = __fadd_rn(acc[3], __fmul_rn(v.w, wq[j][3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (wq[j][e] >= 0.f) acc[e] = __fadd_rn(acc[e], __fmul_rn(yp[e], wq[j][e]));
+      }
+    }
+    float4 o4;
+    o4.x = acc[0] / cnt[0]; o4.y = acc[1] / cnt[1]; o4.z = acc[2] / cnt[2]; o4.w = acc[3] / cnt[3];
+    if (o4.x != o4.x) o4.x = 0.f;   // nan_to_num(nan=0) of 0/0 (utils.py:459)
+    if (o4.y != o4.y) o4.y = 0.f;
+    if (o4.z != o4.z) o4.z = 0.f;
+    if (o4.w != o4.w) o4.w = 0.f;
+    __stcs(reinterpret_cast<float4*>(result + (int64_t)sc * out_len + io), o4);
+  }
+}
+
 extern "C" int sesa_overlap_add(const float* chunk_out, const int64_t* starts, const int64_t* lens,
                                 const int32_t* kinds, int n_chunks, int64_t step, int64_t chunk_size, int fade,
                                 const float* window, int nstems, int channels, int64_t padded_len,
@@ -251,6 +339,24 @@ extern "C" int sesa_overlap_add(const float* chunk_out, const int64_t* starts, c
   const bool vec = (step & 3) == 0 && (chunk_size & 3) == 0 && (crop & 3) == 0 && (out_len & 3) == 0 &&
                    chunk_size <= 8 * step && (reinterpret_cast<uintptr_t>(chunk_out) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(result) & 15) == 0;   // chunk starts are multiples of step
+  const int64_t span64 = ceil_div64(chunk_size, step);   // chunks covering one region
+  if (vec && counter == nullptr && chunk_size < (1ll << 30) && span64 <= 8) {
+    const int bpr = (int)ceil_div64(ceil_div64(step, 4), 256);
+    const int64_t regions = ceil_div64(padded_len, step);
+    const int64_t blocks = regions * bpr;
+    if (blocks < (1ll << 31)) {
+      if (span64 <= 4)
+        overlap_add_region_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            chunk_out, starts, lens, kinds, n_chunks, (int)step, (int)chunk_size, fade, window, nstems * channels, crop,
+            out_len, result, bpr, (int)span64);
+      else
+        overlap_add_region_kernel<8><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            chunk_out, starts, lens, kinds, n_chunks, (int)step, (int)chunk_size, fade, window, nstems * channels, crop,
+            out_len, result, bpr, (int)span64);
+      SESA_LAUNCH_CHECK();
+      return SESA_OK;
+    }
+  }
   if (vec) {
     overlap_add_vec4_kernel<<<(unsigned)ceil_div64(ceil_div64(total, 4), 256), 256, 0, (cudaStream_t)stream>>>(
         chunk_out, starts, lens, kinds, n_chunks, step, chunk_size, fade, window, nstems * channels, padded_len, crop,

@@ -91,50 +91,61 @@ __device__ __forceinline__ void pair_residues(int tid, int& qa, int& qb) {
 // spec[(ns * T + t)][f][c][re/im]  (layout 0 of sesa_stft)
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FT, 3) stft2048_kernel(const float* __restrict__ audio, float* __restrict__ spec,
-                                                      const float* __restrict__ window, const float2* __restrict__ tw,
-                                                      int C, int64_t L, int hop, int T, int fpb) {
-  __shared__ float2 y1[FPAD];
-  __shared__ float2 y2[FPAD];
+                                                         const float* __restrict__ window, const float2* __restrict__ tw,
+                                                         int C, int64_t L, int hop, int T, int fpb) {
+  extern __shared__ float2 smem2k[];
+  float2* y1 = smem2k;
+  float2* y2 = y1 + FPAD;
+  float2* tw1s = y2 + FPAD;        // [FT][17]: W_2048^(tid k), row per thread (padded like y1); in shared memory rather than
+  float2* tw2s = tw1s + FT * 17;   // [8][16]:  W_128^(p k)      registers so that four CTAs fit on an SM
   const int tid = threadIdx.x;
   const int ns = blockIdx.y;
   const int p = tid >> 4, q = tid & 15;
-  float2 tw1[16], tw2[16];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) tw1s[17 * tid + k] = __ldg(tw + tid * k);
+  tw2s[tid] = __ldg(tw + 16 * (tid >> 4) * (tid & 15));
   float win[16];
 #pragma unroll
-  for (int k = 1; k < 16; ++k) {
-    tw1[k] = __ldg(tw + tid * k);          // W_2048^(tid k)
-    tw2[k] = __ldg(tw + 16 * p * k);       // W_128^(p k)
-  }
-#pragma unroll
   for (int m = 0; m < 16; ++m) win[m] = __ldg(window + tid + FT * m);
+  __syncthreads();
   int qa, qb;
   pair_residues(tid, qa, qb);
   const float* a0 = audio + (int64_t)ns * C * L;
   const float* a1 = a0 + L;
   const int t_end = min(T, (int)(blockIdx.x + 1) * fpb);
-  for (int t = blockIdx.x * fpb; t < t_end; ++t) {
-    float2 v[16];
+  // the samples of frame t + 1 are requested while frame t is transformed (one CTA has only four warps to hide the
+  // latency of its own loads)
+  float2 raw[16];
+  auto load_frame = [&](int t) {
     const int64_t base = (int64_t)t * hop - FN / 2 + tid;
     if (base - tid >= 0 && base - tid + FN <= L) {
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const int64_t j = base + FT * m;
-        v[m].x = __ldg(a0 + j) * win[m];
-        v[m].y = C == 2 ? __ldg(a1 + j) * win[m] : 0.f;
+        raw[m].x = __ldg(a0 + j);
+        raw[m].y = C == 2 ? __ldg(a1 + j) : 0.f;
       }
     } else {
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const int64_t j = reflect_index(base + FT * m, L);
-        v[m].x = a0[j] * win[m];
-        v[m].y = C == 2 ? a1[j] * win[m] : 0.f;
+        raw[m].x = a0[j];
+        raw[m].y = C == 2 ? a1[j] : 0.f;
       }
     }
+  };
+  const int t_begin = blockIdx.x * fpb;
+  if (t_begin < t_end) load_frame(t_begin);
+  for (int t = t_begin; t < t_end; ++t) {
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = make_float2(raw[m].x * win[m], raw[m].y * win[m]);
+    if (t + 1 < t_end) load_frame(t + 1);
     // pass 1: radix 16, stride 1
     dft16<false>(v);
     y1[17 * tid] = v[0];
 #pragma unroll
-    for (int k = 1; k < 16; ++k) y1[17 * tid + k] = cmul(v[O16(k)], tw1[k]);
+    for (int k = 1; k < 16; ++k) y1[17 * tid + k] = cmul(v[O16(k)], tw1s[17 * tid + k]);
     __syncthreads();
     // pass 2: radix 16, stride 16
 #pragma unroll
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(FT, 3) stft2048_kernel(const float* __restrict
     dft16<false>(v);
     y2[padi(q + 256 * p)] = v[0];
 #pragma unroll
-    for (int k = 1; k < 16; ++k) y2[padi(q + 256 * p + 16 * k)] = cmul(v[O16(k)], tw2[k]);
+    for (int k = 1; k < 16; ++k) y2[padi(q + 256 * p + 16 * k)] = cmul(v[O16(k)], tw2s[16 * p + k]);
     __syncthreads();
     // pass 3: radix 8, stride 256, on the residues qa and qb = -qa (mod 256)
     float2 a[8], b[8];
@@ -198,22 +209,28 @@ __global__ void __launch_bounds__(FT, 3) stft2048_kernel(const float* __restrict
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Fused complex mask multiply + iSTFT (+ synthesis window, overlap-add over frames, / window envelope, trim).
-// One CTA (128 threads) produces `seg` consecutive output samples of one (chunk, stem): it inverse-transforms every frame
-// overlapping the segment and accumulates in shared memory (deterministic, no global atomics).  Layouts as in stft.cu.
+// One CTA (128 threads) inverse-transforms `G` consecutive frames of one (chunk, stem) — every frame exactly once — and
+// overlap-adds them in a circular shared-memory accumulator of 2 x n_fft samples per channel.  The `hop` samples that no
+// later frame of the CTA touches are flushed after each frame: divided by the window envelope and added to the
+// zero-initialised output with red.global.add.  An output sample receives contributions from at most two CTAs (G is at
+// least (n_fft - hop) / hop), and 0 + a + b == 0 + b + a exactly, so the result does not depend on the order in which
+// the two arrive: the output is bitwise reproducible.  Layouts as in stft.cu.
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int ACC = 2 * FN;   // circular accumulator length per channel
+
 template <int MODE, int C>
 __global__ void __launch_bounds__(FT, 3) mask_istft2048_kernel(
     const float* __restrict__ spec, const float* __restrict__ mask, const int* __restrict__ inv,
     const float* __restrict__ cnt, float* __restrict__ out, const float* __restrict__ window,
-    const float* __restrict__ env, const float2* __restrict__ tw, int hop, int T, int64_t out_len, int seg, int nstems,
+    const float* __restrict__ env, const float2* __restrict__ tw, int hop, int T, int64_t out_len, int G, int nstems,
     int J) {
   extern __shared__ float2 smem2k[];
   float2* y1 = smem2k;
   float2* y2 = smem2k + FPAD;
-  float* acc = reinterpret_cast<float*>(smem2k + 2 * FPAD);   // [C][seg]
+  float* acc = reinterpret_cast<float*>(smem2k + 2 * FPAD);   // [C][ACC]
   constexpr int F = FN / 2 + 1;
   const int tid = threadIdx.x;
-  const int g = blockIdx.x, n = blockIdx.y, b = blockIdx.z;
+  const int n = blockIdx.y, b = blockIdx.z;
   const int nb = gridDim.z;
   const int p = tid >> 4, q = tid & 15;
   float2 tw1[16], tw2[16];
@@ -227,14 +244,24 @@ __global__ void __launch_bounds__(FT, 3) mask_istft2048_kernel(
   for (int m = 0; m < 16; ++m) win[m] = __ldg(window + tid + FT * m) * (1.0f / (float)FN);
   int qa, qb;
   pair_residues(tid, qa, qb);
-  const int64_t i0 = (int64_t)g * seg;
-  const int64_t q0 = i0 + FN / 2;
-  const int64_t q1 = min(q0 + seg, (int64_t)FN / 2 + out_len);
-  for (int i = tid; i < C * seg; i += FT) acc[i] = 0.f;
-  int64_t t_lo = (q0 - FN) / hop + 1;
-  if (q0 - FN < 0) t_lo = 0;
-  int64_t t_hi = (q1 - 1) / hop;
-  if (t_hi > T - 1) t_hi = T - 1;
+  for (int i = tid; i < C * ACC; i += FT) acc[i] = 0.f;
+  const int t_lo = blockIdx.x * G;
+  const int t_hi = min(T, t_lo + G) - 1;
+  float* outp = out + ((int64_t)b * nstems + n) * C * out_len;
+  // flush padded positions [P0, P1): out[P - n_fft/2] += acc / envelope, and clear them for reuse
+  auto flush = [&](int64_t P0, int64_t P1) {
+    for (int64_t P = P0 + tid; P < P1; P += FT) {
+      const int64_t io = P - FN / 2;
+      const int a = (int)(P & (ACC - 1));
+      if (io >= 0 && io < out_len) {
+        const float e = __ldg(env + io);
+        atomicAdd(outp + io, acc[a] / e);
+        if (C == 2) atomicAdd(outp + out_len + io, acc[ACC + a] / e);
+      }
+      acc[a] = 0.f;
+      if (C == 2) acc[ACC + a] = 0.f;
+    }
+  };
 
   // masked spectrum of bin f for both channels: (YL, YR)
   auto load_bin = [&](int64_t row, int f, float2& yl, float2& yr) {
@@ -291,7 +318,7 @@ __global__ void __launch_bounds__(FT, 3) mask_istft2048_kernel(
   auto z_lo = [](float2 yl, float2 yr) { return make_float2(yl.x - yr.y, yl.y + yr.x); };
   auto z_hi = [](float2 yl, float2 yr) { return make_float2(yl.x + yr.y, yr.x - yl.y); };
 
-  for (int64_t t = t_lo; t <= t_hi; ++t) {
+  for (int t = t_lo; t <= t_hi; ++t) {
     const int64_t row = (int64_t)b * T + t;
     // a[k] = Z[qa + 256 k], b[k] = Z[qb + 256 k], k = 0..7, built from bins f <= 1024 only
     float2 a[8], bb[8];
@@ -334,6 +361,9 @@ __global__ void __launch_bounds__(FT, 3) mask_istft2048_kernel(
       y2[padi(qb + 256 * m)] = bb[O8(m)];
     }
     __syncthreads();
+    // the previous frame's hop is final for this CTA (its accumulation precedes the barrier above, no later frame reaches
+    // back before t * hop)
+    if (t > t_lo) flush((int64_t)(t - 1) * hop, (int64_t)t * hop);
     // transposed pass 2: gather from the forward scatter positions, conj twiddle, radix 16, scatter to tid + 128 m
     float2 v[16];
     v[0] = y2[padi(q + 256 * p)];
@@ -354,31 +384,20 @@ __global__ void __launch_bounds__(FT, 3) mask_istft2048_kernel(
       v[k] = cmulw<true>(x, tw1[k].x, tw1[k].y);
     }
     dft16<true>(v);
-    // v[O16(m)] = z[tid + 128 m]: windowed overlap-add of the part of this frame inside the segment
-    const int64_t fq = t * hop;
-    const int lo = (int)max((int64_t)0, q0 - fq);
-    const int hi = (int)min((int64_t)FN, q1 - fq);
-    const int o0 = (int)(fq - q0);
+    // v[O16(m)] = z[tid + 128 m]: windowed overlap-add into the circular accumulator
+    const int fq = (int)(((int64_t)t * hop) & (ACC - 1));
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-      const int i = tid + FT * m;
-      if (i >= lo && i < hi) {
-        const float2 z = v[O16(m)];
-        acc[o0 + i] += z.x * win[m];
-        if (C == 2) acc[seg + o0 + i] += z.y * win[m];
-      }
+      const int a = (fq + tid + FT * m) & (ACC - 1);
+      const float2 z = v[O16(m)];
+      acc[a] += z.x * win[m];
+      if (C == 2) acc[ACC + a] += z.y * win[m];
     }
     // no barrier here: the next frame's y2 scatter follows this frame's second barrier (every y2 gather precedes it), its
-    // y1 scatter and its accumulation follow its own barriers, which every thread reaches only after finishing this frame
+    // y1 scatter, its flush and its accumulation follow its own barriers, which every thread reaches only after this frame
   }
   __syncthreads();
-  const int nvalid = (int)(q1 - q0);
-  for (int i = tid; i < nvalid; i += FT) {
-    const float e = env[i0 + i];
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-      out[(((int64_t)b * nstems + n) * C + c) * out_len + i0 + i] = acc[c * seg + i] / e;
-  }
+  if (t_hi >= t_lo) flush((int64_t)t_hi * hop, (int64_t)t_hi * hop + FN);
 }
 
 }  // namespace
@@ -391,13 +410,19 @@ int sesa_launch_stft2048(const float* audio, float* spec, const float* window, c
     SESA_CUDA(cudaGetDevice(&dev));
     SESA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  // enough CTAs to fill every SM about three times over, at most 16 frames per CTA (consecutive frames of a CTA re-read
+  // enough CTAs to fill every SM three times over (the residency limit), at most 16 frames per CTA (consecutive frames of a CTA re-read
   // most of their samples from L1)
   int fpb = (int)ceil_div64((int64_t)T * n_signals, (int64_t)sms * 3);
   if (fpb < 1) fpb = 1;
   if (fpb > 16) fpb = 16;
   dim3 grid((unsigned)ceil_div64(T, fpb), n_signals);
-  stft2048_kernel<<<grid, FT, 0, stream>>>(audio, spec, window, reinterpret_cast<const float2*>(twiddle), channels,
+  const size_t smem = (size_t)(2 * FPAD + FT * 17 + 8 * 16) * sizeof(float2);
+  static bool configured = false;
+  if (!configured) {
+    SESA_CUDA(cudaFuncSetAttribute(stft2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  stft2048_kernel<<<grid, FT, smem, stream>>>(audio, spec, window, reinterpret_cast<const float2*>(twiddle), channels,
                                            length, hop, T, fpb);
   SESA_LAUNCH_CHECK();
   return SESA_OK;
@@ -406,11 +431,11 @@ int sesa_launch_stft2048(const float* audio, float* spec, const float* window, c
 template <int MODE, int C>
 static int launch_istft_mc(const float* spec, const float* mask, const int* inv, const float* cnt, float* out,
                            const float* window, const float* env, const float* tw, int batch, int nstems, int hop, int T,
-                           int64_t out_len, int n_gathered, int seg, size_t smem, cudaStream_t stream) {
+                           int64_t out_len, int n_gathered, int G, size_t smem, cudaStream_t stream) {
   SESA_CUDA(cudaFuncSetAttribute(mask_istft2048_kernel<MODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div64(out_len, seg), nstems, batch);
+  dim3 grid((unsigned)ceil_div64(T, G), nstems, batch);
   mask_istft2048_kernel<MODE, C><<<grid, FT, smem, stream>>>(spec, mask, inv, cnt, out, window, env,
-                                                            reinterpret_cast<const float2*>(tw), hop, T, out_len, seg,
+                                                            reinterpret_cast<const float2*>(tw), hop, T, out_len, G,
                                                             nstems, n_gathered);
   SESA_LAUNCH_CHECK();
   return SESA_OK;
@@ -420,17 +445,24 @@ int sesa_launch_mask_istft2048(const float* spec, const float* mask, const int* 
                                const float* window, const float* env, const float* twiddle, int batch, int nstems,
                                int channels, int hop, int T, int64_t out_len, int mode, int n_gathered,
                                cudaStream_t stream) {
-  // segment = G hops; (G + n_fft/hop - 1) / G of the transforms are redundant, so G is as large as three CTAs per SM allow
-  const size_t fft_bytes = (size_t)2 * FPAD * sizeof(float2);
-  int G = 12;
-  while (G > 1 && fft_bytes + (size_t)channels * G * hop * sizeof(float) > 74 * 1024) --G;
-  const int seg = G * hop;
-  const size_t smem = fft_bytes + (size_t)channels * seg * sizeof(float);
-  SESA_CHECK_ARG(smem <= 200 * 1024, "sesa_mask_istft: segment does not fit in shared memory");
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    SESA_CUDA(cudaGetDevice(&dev));
+    SESA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // frames per CTA: one resident wave (three CTAs per SM) when the launch is small, at most 16; never fewer than
+  // (n_fft - hop) / hop, so that an output sample is shared by at most two CTAs (see the kernel comment)
+  const int g_min = (FN - hop + hop - 1) / hop;
+  int G = (int)ceil_div64((int64_t)T * nstems * batch, (int64_t)sms * 3);
+  if (G > 16) G = 16;
+  if (G < g_min) G = g_min;
+  const size_t smem = (size_t)2 * FPAD * sizeof(float2) + (size_t)channels * ACC * sizeof(float);
+  SESA_CUDA(cudaMemsetAsync(out, 0, (size_t)batch * nstems * channels * out_len * sizeof(float), stream));
 #define SESA_ISTFT_CASE(M, CC)                                                                                       \
   if (mode == M && channels == CC)                                                                                   \
     return launch_istft_mc<M, CC>(spec, mask, inv, cnt, out, window, env, twiddle, batch, nstems, hop, T, out_len,    \
-                                  n_gathered, seg, smem, stream);
+                                  n_gathered, G, smem, stream);
   SESA_ISTFT_CASE(0, 1) SESA_ISTFT_CASE(0, 2) SESA_ISTFT_CASE(1, 1) SESA_ISTFT_CASE(1, 2) SESA_ISTFT_CASE(2, 1)
   SESA_ISTFT_CASE(2, 2)
 #undef SESA_ISTFT_CASE

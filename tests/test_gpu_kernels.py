@@ -505,3 +505,43 @@ def test_instnorm_and_norm_act_split(lib):
     gqd = gq.to(dev)
     lib.call('sesa_transpose_add', P(x2), P(gqd), B * T, F, C, C, S())
     assert torch.allclose(x2.cpu(), x + gq.reshape(B, T, C, F).permute(0, 1, 3, 2))
+
+
+@pytest.mark.parametrize('length,L,ov,nc', [(4000, 1000, 1, 2), (40000, 4000, 4, 2), (40004, 4000, 4, 1), (52000, 8000, 2, 4),
+                                             (8 * 4410 + 1236, 4416, 4, 2), (100000, 4800, 8, 2), (1000, 1000, 2, 2)])
+def test_overlap_add_region_kernel_is_bit_identical_to_the_scalar_gather(lib, length, L, ov, nc):
+    """The product path (no counter -> region kernel with block-uniform chunk lists) must reproduce the scalar gather
+    bit for bit: chunk order, separate multiply and add, divide by the window sum (utils.py:439-464)."""
+    from sesa_audio_separation_b200.plan import make_plan, windowing_array
+    dev = 'cuda'
+    plan = make_plan(length, L, ov, 1)
+    g = torch.Generator(device=dev).manual_seed(length + L + ov)
+    y = torch.randn(plan.n_chunks, nc, L, device=dev, generator=g)
+    starts = torch.tensor(plan.starts, dtype=torch.int64, device=dev)
+    lens = torch.tensor(plan.lens, dtype=torch.int64, device=dev)
+    kinds = torch.tensor(plan.kinds, dtype=torch.int32, device=dev)
+    window = windowing_array(L, plan.fade).to(dev)
+    crop = plan.border if plan.pad else 0
+    a = torch.full((nc, length), 7.0, device=dev)
+    b = torch.full((nc, length), 9.0, device=dev)
+    counter = torch.empty(plan.padded, device=dev)
+    lib.call('sesa_overlap_add', P(y), P(starts), P(lens), P(kinds), plan.n_chunks, plan.step, L, plan.fade, P(window), 1, nc,
+             plan.padded, crop, length, P(a), P(counter), S())
+    lib.call('sesa_overlap_add', P(y), P(starts), P(lens), P(kinds), plan.n_chunks, plan.step, L, plan.fade, P(window), 1, nc,
+             plan.padded, crop, length, P(b), None, S())
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    # and against a plain torch statement of the reference loop
+    res = torch.zeros(nc, plan.padded, device=dev)
+    cnt = torch.zeros(plan.padded, device=dev)
+    for k in range(plan.n_chunks):
+        s, n = plan.starts[k], plan.lens[k]
+        w = window.clone()
+        if plan.kinds[k] == 1:
+            w[:plan.fade] = 1
+        elif plan.kinds[k] == 2:
+            w[-plan.fade:] = 1
+        res[:, s:s + n] += y[k, :, :n] * w[:n]
+        cnt[s:s + n] += w[:n]
+    ref = torch.nan_to_num((res / cnt)[:, crop:crop + length], nan=0.0)
+    assert torch.equal(ref, b)

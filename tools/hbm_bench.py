@@ -46,7 +46,7 @@ def main():
     ap.add_argument('--only', default='')
     args = ap.parse_args()
     _lib.require_cuda()
-    lib = _lib.load()
+    _lib.load()
     dev = 'cuda'
     S = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     B, C, L, N, hop, NS = args.chunks, 2, 352800, 2048, 441, args.stems
@@ -68,12 +68,12 @@ def main():
         print(f'{name:12s} {ms * 1e3:9.1f} us  {nbytes / 1e6:9.1f} MB  {gbs:8.1f} GB/s  {gbs / HBM_PEAK * 100:5.1f} % of {HBM_PEAK:.0f}', flush=True)
 
     if not args.only or 'stft' in args.only.split(','):
-        ms = timed(lambda: lib.call('sesa_stft', P(audio), P(spec), P(win), P(tw), B, C, L, N, hop, 0, F, S), args.reps, flush)
+        ms = timed(lambda: _lib.call('sesa_stft', P(audio), P(spec), P(win), P(tw), B, C, L, N, hop, 0, F, S), args.reps, flush)
         report('stft', ms, B * (4 * C * L + 8 * C * F * T))
     else:
-        lib.call('sesa_stft', P(audio), P(spec), P(win), P(tw), B, C, L, N, hop, 0, F, S)
+        _lib.call('sesa_stft', P(audio), P(spec), P(win), P(tw), B, C, L, N, hop, 0, F, S)
     if not args.only or 'istft' in args.only.split(','):
-        ms = timed(lambda: lib.call('sesa_mask_istft', P(spec), P(mask), None, None, P(out), P(win), P(env), P(tw), B, NS, C, N,
+        ms = timed(lambda: _lib.call('sesa_mask_istft', P(spec), P(mask), None, None, P(out), P(win), P(env), P(tw), B, NS, C, N,
                                     hop, T, L, 0, 0, S), args.reps, flush)
         report('mask_istft', ms, B * (8 * C * F * T + NS * (8 * C * F * T + 4 * C * L)))
     # demix overlap-add over a whole track
@@ -88,13 +88,13 @@ def main():
         result = torch.empty(NS, C, length, device=dev)
         window = windowing_array(L, plan.fade).to(dev)
         crop = plan.border if plan.pad else 0
-        ms = timed(lambda: lib.call('sesa_overlap_add', P(chunk_out), P(starts), P(lens), P(kinds), plan.n_chunks, plan.step, L,
+        ms = timed(lambda: _lib.call('sesa_overlap_add', P(chunk_out), P(starts), P(lens), P(kinds), plan.n_chunks, plan.step, L,
                                     plan.fade, P(window), NS, C, plan.padded, crop, length, P(result), None, S), args.reps, flush)
         report('overlap_add', ms, 4 * NS * C * (L * plan.n_chunks + length))
     if not args.only or 'frame' in args.only.split(','):
         padded = torch.randn(C, plan.padded, device=dev, generator=g)
         chunks = torch.empty(B, C, L, device=dev)
-        ms = timed(lambda: lib.call('sesa_frame_chunks', P(padded), plan.padded, C, P(starts), P(lens), P(modes), B, L, P(chunks),
+        ms = timed(lambda: _lib.call('sesa_frame_chunks', P(padded), plan.padded, C, P(starts), P(lens), P(modes), B, L, P(chunks),
                                     S), args.reps, flush)
         report('framing', ms, 2 * 4 * B * C * L)
     torch.cuda.synchronize()
