@@ -250,6 +250,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       hi = row_valid ? lo + p.seq_len : 0;
       out_row = row_base + i;
     }
+    // the gate logit of this (row, head) is only needed at the very end: request it now so its latency is never exposed
+    const float gl = row_valid ? __ldg(p.gates + out_row * p.ldg + h) : 0.f;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     constexpr int HC = BKV / 2;   // 32 score columns / output dims per thread
     float o[HC];
@@ -326,7 +328,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
     pair_barrier(warp & 3);
     const float ltot = lrun + xs[(hf ^ 1) * BQ + i];
     if (row_valid) {
-      const float gl = p.gates[out_row * p.ldg + h];
       const float sc = (1.0f / (1.0f + expf(-gl))) / ltot;
       __nv_bfloat16* op = p.out + out_row * p.ldo + h * DH + hf * HC;
 #pragma unroll

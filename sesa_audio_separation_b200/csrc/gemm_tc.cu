@@ -68,7 +68,8 @@ struct Cfg {
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFF = EPI_OFF + EPI_WARPS * EPI_STAGE_BYTES;   // per-warp bias slice of the tile (BN / NCH floats)
   static constexpr int BAR_OFF = BIAS_OFF + BN * 4 * 4;
-  static constexpr int TILE_OFF = BAR_OFF + 256;
+  static constexpr int GRP_OFF = BAR_OFF + 256;                // copy of the group record of single-problem launches
+  static constexpr int TILE_OFF = GRP_OFF + (int)sizeof(TcGroup);
   static constexpr int SMEM_BYTES = TILE_OFF + MAX_GROUPS * 4 + 1024 /*alignment slack*/;
   static constexpr int TMEM_COLS = 2 * BN;                  // 256 or 512: power of two
 };
@@ -179,6 +180,12 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
   const int lane = threadIdx.x & 31;
 
   for (int i = threadIdx.x; i < n_groups; i += NUM_THREADS) tile_end[i] = groups[i].tile_end;
+  // single-problem launches (every transformer GEMM): the epilogue warps read the problem record from shared memory
+  // instead of chasing it through L2 at the start of every tile
+  const TcGroup* g_local = reinterpret_cast<const TcGroup*>(smem + C::GRP_OFF);
+  if (n_groups == 1)
+    for (int i = threadIdx.x; i < (int)(sizeof(TcGroup) / 4); i += NUM_THREADS)
+      reinterpret_cast<uint32_t*>(smem + C::GRP_OFF)[i] = reinterpret_cast<const uint32_t*>(groups)[i];
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       tc::mbar_init(&full_bar[s], 1);
@@ -312,6 +319,8 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     // per-element arithmetic works on float4s with per-lane constants (bias quad, rotary quad).
     const int ew = warp - 2;
     const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    int two_planes;                  // kept in a register: re-reading the kernel parameter inside the store loop stalls on LDC
+    asm volatile("mov.u32 %0, %1;" : "=r"(two_planes) : "r"(out_planes > 1 ? 1 : 0));
     const int ch = ew >> 2;          // which half of the tile's columns
     constexpr int HALF = BN / NCH;   // columns per epilogue warp
     const uint32_t stage = tc::smem_u32(smem + C::EPI_OFF + ew * EPI_STAGE_BYTES);   // byte address in shared space
@@ -326,7 +335,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     int as = 0;
     uint32_t aph = 0;
     for (int tile = unit; tile < total_tiles; tile += n_units) {
-      const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
+      const TcGroup* g = n_groups == 1 ? g_local : &groups[find_group(tile_end, n_groups, tile)];
       const int t = tile - g->tile_begin;
       const int mb = (t / g->n_blocks) * CG + cta_rank, nb = t % g->n_blocks;
       const int M = g->M, N = g->N;
@@ -428,21 +437,24 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       // the accumulator columns of step c + 1 are requested from TMEM while step c is being finished
       float v[EPI_COLS];
       if (n_half < N) tmem_ld16(t_row, v);
+      float4 cs4[4];
+      auto load_rot = [&](int cstep) {   // (cos, sin) pairs of this lane's two column pairs at its four rows' positions
+        const int nn = n_half + cstep * EPI_COLS;
+        if ((FLAVOR == F_ROT || kGeneric) && cstep < HALF / EPI_COLS && nn < rot_cols && nn < N) {
+          const int rd = ((nn + c4 * 4) % ep.rot_dim) >> 1;
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            cs4[it] = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rd) >> 1));
+        }
+      };
+      load_rot(0);
 #pragma unroll 1
       for (int c = 0; c < HALF / EPI_COLS; ++c) {
         const int n = n_half + c * EPI_COLS;
         if (n >= N) break;  // warp-uniform
         const int colb = n + c4 * 4;
-        // rotary (cos, sin) quads of this lane's 4 rows: issued before the transpose so that their latency hides under
-        // phase A
-        const bool do_rot = n < rot_cols;
-        float4 cs4[4];
-        if (do_rot) {
-          const int rd = (colb % ep.rot_dim) >> 1;
-#pragma unroll
-          for (int it = 0; it < 4; ++it)
-            cs4[it] = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rd) >> 1));
-        }
+        // rotary (cos, sin) quads of this lane's 4 rows were requested during the previous step (after its rotation)
+        const bool do_rot = (FLAVOR == F_ROT || kGeneric) && n < rot_cols;
         // ---- phase A
         tc::tmem_ld_wait();
 #pragma unroll
@@ -504,6 +516,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               o[it].w = x4 * cs.z + x3 * cs.w;
             }
           }
+          load_rot(c + 1);   // cs4 is dead from here on: the next step's constants travel under the stores and phase A
           if (residual) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) { o[it].x += res[it].x; o[it].y += res[it].y; o[it].z += res[it].z; o[it].w += res[it].w; }
@@ -521,7 +534,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               if (ok4[it]) {
                 __nv_bfloat16* pr = Pp + orow4[it] * ldp + colb;
                 *reinterpret_cast<uint2*>(pr) = make_uint2(h0, h1);
-                if (out_planes > 1) *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(l0, l1);
+                if (two_planes) *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(l0, l1);
               }
             }
           }
@@ -564,8 +577,8 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               }
               if (Pp != nullptr) {
                 __nv_bfloat16 h, l;
-                if (colb + 1 < N) { tc::split_bf16(g0, h, l); Pp[orow * ldp + oc] = h; if (out_planes > 1) Pp[orow * ldp + p_plane + oc] = l; }
-                if (colb + 3 < N) { tc::split_bf16(g1, h, l); Pp[orow * ldp + oc + 1] = h; if (out_planes > 1) Pp[orow * ldp + p_plane + oc + 1] = l; }
+                if (colb + 1 < N) { tc::split_bf16(g0, h, l); Pp[orow * ldp + oc] = h; if (two_planes) Pp[orow * ldp + p_plane + oc] = l; }
+                if (colb + 3 < N) { tc::split_bf16(g1, h, l); Pp[orow * ldp + oc + 1] = h; if (two_planes) Pp[orow * ldp + p_plane + oc + 1] = l; }
               }
               continue;
             }
@@ -583,10 +596,11 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
                 __nv_bfloat16 h, l;
                 tc::split_bf16(val, h, l);
                 Pp[orow * ldp + colb + e] = h;
-                if (out_planes > 1) Pp[orow * ldp + p_plane + colb + e] = l;
+                if (two_planes) Pp[orow * ldp + p_plane + colb + e] = l;
               }
             }
           }
+          load_rot(c + 1);
         }
         if (!kEarlyLd && more) tmem_ld16(t_row + (c + 1) * EPI_COLS, v);
         __syncwarp();
