@@ -12,8 +12,11 @@
 //                 block-diagonal mask (band attention, seq 62 -> 2 sequences per tile).
 // Per KV block: S = Q K^T (UMMA 128x64x64) -> TMEM; the 128 softmax threads (thread = row) read S, do the online
 // softmax in fp32, write P as packed bf16 hi/lo back into TENSOR MEMORY (tcgen05.st); O_blk = P V (UMMA 128x64x64 with
-// A read from TMEM and V as the MN-major shared-memory operand, K/V blocks double-buffered by TMA) -> TMEM; threads fold O_blk into their fp32 running output.  fp32 parity uses the same
-// three-product split as the GEMM (hi.hi + hi.lo + lo.hi).  Two CTAs are resident per SM so one CTA's softmax
+// A read from TMEM and V as the MN-major shared-memory operand, K/V blocks double-buffered by TMA) accumulates into ONE
+// fp32 O tile that stays in tensor memory for the whole sequence.  The exponent offset of a row only follows the running
+// maximum when it grew by more than 2^8 ("lazy rescaling"): then, and only then, the threads of that warp pair rescale
+// their O columns in TMEM; in the common case a block costs the softmax threads no accumulator work at all.
+// fp32 parity uses the same three-product split as the GEMM (hi.hi + hi.lo + lo.hi).  Two CTAs are resident per SM so one CTA's softmax
 // overlaps the other's MMAs.
 #include "common.cuh"
 #include "sesa_b200.h"
@@ -24,7 +27,7 @@ namespace {
 constexpr int DH = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 64;
-constexpr int SM_THREADS = 256;   // warps 0-7: softmax / accumulate; thread (row = (warp&3)*32+lane, half = warp>>2)
+constexpr int SM_THREADS = 256;   // warps 0-7: softmax; thread (row = (warp&3)*32+lane, half = warp>>2)
 constexpr int ATT_THREADS = SM_THREADS + 64;  // warp 8: MMA issue, warp 9: TMA producer
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -67,7 +70,7 @@ struct ACfg {
   static constexpr int OFF_X = OFF_V + KV_STAGES * NP * KV_BYTES;   // float xch[2][2][128]: row max / row sum exchange
   static constexpr int OFF_BAR = OFF_X + 2 * 2 * BQ * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  // TMEM columns: SP[0] [0,64) | SP[1] [64,128) | O[0] [128,192) | O[1] [192,256).
+  // TMEM columns: SP[0] [0,64) | SP[1] [64,128) | O [128,192).
   // SP[b] holds the fp32 scores of block j (b = j&1) and is overwritten IN PLACE by P (bf16 pairs: hi in the first
   // 32 columns, lo in the last 32) once both threads of a row have read their scores.
   static constexpr int TMEM_COLS = 256;
@@ -123,7 +126,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_SP = tmem_base;         // + 64*b
-  const uint32_t tmem_O = tmem_base + 128;    // + 64*b
+  const uint32_t tmem_O = tmem_base + 128;
 
   // ---- work item geometry
   int nblk, q0 = 0;
@@ -210,7 +213,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       for (int j = 0; j < nblk; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        tc::mbar_wait(&p_full[st], ph);       // P_j is in TMEM (S_j consumed); O[st] of block j-2 has been read
+        tc::mbar_wait(&p_full[st], ph);       // P_j is in TMEM (S_j consumed); any rescale of O is complete
         tc::mbar_wait(&v_full[st], ph);
         tc::tc_fence_after();
 #pragma unroll
@@ -219,8 +222,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
           const uint32_t va = aV + (st * C::NP + (prod == 1 ? 1 : 0)) * C::KV_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BKV / 16; ++ks)   // 16 keys = 8 packed TMEM columns of P, 16 rows (2 KB) of V
-            tc::umma_f16_ts(tmem_O + st * 64, pa + ks * 8, tc::make_smem_desc_sw128(va + ks * 2048, 8192), idesc_o,
-                            (prod | ks) != 0 ? 1u : 0u);
+            tc::umma_f16_ts(tmem_O, pa + ks * 8, tc::make_smem_desc_sw128(va + ks * 2048, 8192), idesc_o,
+                            (j | prod | ks) != 0 ? 1u : 0u);
         }
         tc::umma_commit(&o_full[st]);
         tc::umma_commit(&v_empty[st]);
@@ -230,9 +233,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
   } else {
     // ================= softmax / accumulate threads =================
     // Two threads per query row: thread (row i, half hf) owns keys [32 hf, 32 hf + 32) of every 64-key block and
-    // output dims [32 hf, 32 hf + 32).  The row maximum is agreed through shared memory once per block.
-    // Order per thread: softmax_0, [softmax_j, accumulate_{j-1}] ..., accumulate_{last}: the P V MMA of block j-1
-    // runs under the softmax of block j.
+    // output dims [32 hf, 32 hf + 32).  The row maximum is agreed through shared memory once per block.  O accumulates in
+    // tensor memory; the threads touch it only to rescale (rare) and to read the finished tile.
     const int hf = warp >> 2;
     const int i = (warp & 3) * 32 + (tid & 31);   // row of the tile == TMEM lane
     int lo = 0, hi = p.seq_len;                   // valid key range (tile-relative key index)
@@ -254,22 +256,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
     const float gl = row_valid ? __ldg(p.gates + out_row * p.ldg + h) : 0.f;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     constexpr int HC = BKV / 2;   // 32 score columns / output dims per thread
-    float o[HC];
-#pragma unroll
-    for (int d = 0; d < HC; ++d) o[d] = 0.f;
-    float mrun = -INFINITY, lrun = 0.f, corr_prev = 0.f;
-
-    auto accumulate = [&](int jb) {   // o = o * corr(jb) + O_blk(jb)
-      const int st = jb & 1;
-      tc::mbar_wait(&o_full[st], (jb >> 1) & 1);
-      tc::tc_fence_after();
-      float ob[HC];
-      tc::tmem_ld32(tmem_O + st * 64 + lane_off + hf * HC, ob);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int d = 0; d < HC; ++d) o[d] = fmaf(o[d], corr_prev, ob[d]);
-      tc::tc_fence_before();
-    };
+    float mref = -INFINITY, lrun = 0.f;   // exponent reference of the row (lags the true maximum by at most 2^8), row sum
 
     for (int j = 0; j < nblk; ++j) {
       const int st = j & 1;
@@ -298,9 +285,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       // "both halves of every row have read their scores" before P overwrites them in place)
       pair_barrier(warp & 3);
       tc::tc_fence_after();
-      const float mnew = fmaxf(mrun, fmaxf(mx, xm[(hf ^ 1) * BQ + i]));
-      const float moff = (mnew == -INFINITY ? 0.f : mnew) * LOG2E;
-      const float corr = tc::ex2_approx(fmaf(mrun, LOG2E, -moff));
+      const float mnew = fmaxf(mref, fmaxf(mx, xm[(hf ^ 1) * BQ + i]));
+      // lazy rescaling: keep the old reference while exp2 arguments stay below 8 (p < 256: harmless for the bf16 split
+      // and the fp32 accumulators).  Both threads of a row take the same decision from the same numbers.
+      const bool grow = (mnew - mref) * LOG2E > 8.0f;   // also true for the first finite maximum (mref = -inf)
+      if (__any_sync(0xffffffffu, grow)) {
+        const float corr = grow ? tc::ex2_approx((mref - mnew) * LOG2E) : 1.0f;   // exp2(-inf) = 0 on the first block
+        if (j > 0) {
+          // rows of this warp moved their reference: rescale our 32 columns of O once every earlier P V has retired
+          tc::mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc::tc_fence_after();
+          float ob[HC];
+          tc::tmem_ld32(tmem_O + lane_off + hf * HC, ob);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < HC; ++d) ob[d] *= corr;
+          tc::tmem_st32(tmem_O + lane_off + hf * HC, reinterpret_cast<const uint32_t*>(ob));
+        }
+        lrun *= corr;
+        if (grow) mref = mnew;
+      }
+      const float moff = (mref == -INFINITY ? 0.f : mref) * LOG2E;
       float sum = 0.f;
       uint32_t phi[HC / 2], plo[HC / 2];
 #pragma unroll
@@ -313,14 +318,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       tc::tmem_st16(tmem_SP + st * 64 + lane_off + hf * (HC / 2), phi);
       if (NSPLIT == 3) tc::tmem_st16(tmem_SP + st * 64 + lane_off + 32 + hf * (HC / 2), plo);
       tc::tmem_st_wait();
-      lrun = lrun * corr + sum;
-      mrun = mnew;
+      lrun += sum;
       tc::tc_fence_before();
       tc::mbar_arrive(&p_full[st]);
-      if (j > 0) accumulate(j - 1);
-      corr_prev = corr;
     }
-    accumulate(nblk - 1);
+    // the finished O tile
+    float o[HC];
+    tc::mbar_wait(&o_full[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
+    tc::tc_fence_after();
+    tc::tmem_ld32(tmem_O + lane_off + hf * HC, o);
+    tc::tmem_ld_wait();
+    tc::tc_fence_before();
 
     // combine the two halves' row sums, gate, split to planes, store this thread's 32 output dims
     float* xs = xch + ((nblk & 1) * 2) * BQ;
