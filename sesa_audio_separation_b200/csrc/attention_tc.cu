@@ -257,10 +257,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     constexpr int HC = BKV / 2;   // 32 score columns / output dims per thread
     float mref = -INFINITY, lrun = 0.f;   // exponent reference of the row (lags the true maximum by at most 2^8), row sum
+    // a warp whose 32 rows all lie beyond the sequence (the last query tile of 801 = 6 x 128 + 33 rows) only keeps the
+    // barrier protocol going: its P rows are never stored, so their content does not matter
+    const bool warp_active = __any_sync(0xffffffffu, row_valid);
 
     for (int j = 0; j < nblk; ++j) {
       const int st = j & 1;
       tc::mbar_wait(&s_full[st], (j >> 1) & 1);
+      if (!warp_active) {
+        tc::mbar_arrive(&p_full[st]);
+        continue;
+      }
       tc::tc_fence_after();
       float s[HC];
       tc::tmem_ld32(tmem_SP + st * 64 + lane_off + hf * HC, s);
@@ -324,11 +331,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
     }
     // the finished O tile
     float o[HC];
+    if (warp_active) {
     tc::mbar_wait(&o_full[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
     tc::tc_fence_after();
     tc::tmem_ld32(tmem_O + lane_off + hf * HC, o);
     tc::tmem_ld_wait();
     tc::tc_fence_before();
+    }
 
     // combine the two halves' row sums, gate, split to planes, store this thread's 32 output dims
     float* xs = xch + ((nblk & 1) * 2) * BQ;
