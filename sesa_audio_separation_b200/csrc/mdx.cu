@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(256) instnorm_acc_kernel(const float* __restri
   const int64_t i0 = (int64_t)blockIdx.x * chunk;
   const int64_t i1 = min(n1, i0 + chunk);
   if (layout == 0) {
-    // threads = (channel quads) x (position lanes): float4 loads, 512 contiguous bytes per warp and position
+    // threads = (channel quads) x (position lanes): float4 loads, 512 contiguous bytes per warp and position; four
+    // positions in flight per thread (the loop is latency-bound otherwise: deep layers have few positions per block)
     __shared__ float red[256][8];
     const int cq = C >> 2;                               // C % 4 == 0 (checked by the host entry)
     const int nq = cq < 256 ? cq : 256;                  // channel quads handled per pass
@@ -51,8 +52,22 @@ __global__ void __launch_bounds__(256) instnorm_acc_kernel(const float* __restri
       float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
       if (qd < cq && tl < lanes) {
         const float* p = x + ((int64_t)b * n1 + i0 + tl) * ld + 4 * qd;
-        for (int64_t i = i0 + tl; i < i1; i += lanes, p += (int64_t)lanes * ld) {
-          const float4 v = *reinterpret_cast<const float4*>(p);
+        const int64_t stride = (int64_t)lanes * ld;
+        int64_t i = i0 + tl;
+        for (; i + 3 * lanes < i1; i += 4 * lanes, p += 4 * stride) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + stride));
+          const float4 v2 = __ldg(reinterpret_cast<const float4*>(p + 2 * stride));
+          const float4 v3 = __ldg(reinterpret_cast<const float4*>(p + 3 * stride));
+          s[0] += (v0.x + v1.x) + (v2.x + v3.x); s[1] += (v0.y + v1.y) + (v2.y + v3.y);
+          s[2] += (v0.z + v1.z) + (v2.z + v3.z); s[3] += (v0.w + v1.w) + (v2.w + v3.w);
+          ss[0] += fmaf(v0.x, v0.x, v1.x * v1.x) + fmaf(v2.x, v2.x, v3.x * v3.x);
+          ss[1] += fmaf(v0.y, v0.y, v1.y * v1.y) + fmaf(v2.y, v2.y, v3.y * v3.y);
+          ss[2] += fmaf(v0.z, v0.z, v1.z * v1.z) + fmaf(v2.z, v2.z, v3.z * v3.z);
+          ss[3] += fmaf(v0.w, v0.w, v1.w * v1.w) + fmaf(v2.w, v2.w, v3.w * v3.w);
+        }
+        for (; i < i1; i += lanes, p += stride) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p));
           s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
           ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]);
           ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
@@ -74,24 +89,54 @@ __global__ void __launch_bounds__(256) instnorm_acc_kernel(const float* __restri
       __syncthreads();
     }
   } else {
-    // one warp per (i, c) row of n2 contiguous values
+    // rows of n2 contiguous values, one per (position, channel).  A row is read by the smallest power-of-two lane group
+    // that covers it with 128-bit loads (deep layers have rows of 8-64 values: 2-16 lanes), so a warp sums 32/g rows at a
+    // time; each row sum goes to its channel's fp64 accumulator.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int c = warp; c < C; c += nw) {
+    const bool vec = (n2 & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const int n4 = vec ? n2 >> 2 : n2;          // loads per row
+    int g = 1;
+    while (g < n4 && g < 32) g <<= 1;
+    const int rpw = 32 / g, sub = lane / g, lj = lane % g;
+    // layout 1: `chunk` counts ROWS (position-major, channel-minor) per block, so deep layers with a handful of positions
+    // still spread over the machine
+    const int64_t row_end = min(n1 * C, i0 + chunk);
+    const int64_t per_pass = (int64_t)nw * rpw;
+    for (int64_t r0 = i0; r0 < row_end; r0 += per_pass) {     // block-uniform trip count (full-mask shuffles below)
+      const int64_t r = r0 + warp * rpw + sub;
+      const bool ok = r < row_end;
+      const int c = ok ? (int)(r % C) : 0;
+      const int64_t i = ok ? r / C : 0;
+      const float* p = x + (((int64_t)b * n1 + i) * C + c) * n2;
       float s = 0.f, ss = 0.f;
-      for (int64_t i = i0; i < i1; ++i) {
-        const float* p = x + (((int64_t)b * n1 + i) * C + c) * n2;
-        for (int j = lane; j < n2; j += 32) {
-          const float v = p[j];
-          s += v;
-          ss = fmaf(v, v, ss);
+      if (ok) {
+        if (vec) {
+          const float4* p4 = reinterpret_cast<const float4*>(p);
+          int j = lj;
+          for (; j + g < n4; j += 2 * g) {
+            const float4 v0 = __ldg(p4 + j), v1 = __ldg(p4 + j + g);
+            s += (v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w);
+            ss += fmaf(v0.x, v0.x, v0.y * v0.y) + fmaf(v0.z, v0.z, v0.w * v0.w) + fmaf(v1.x, v1.x, v1.y * v1.y) +
+                  fmaf(v1.z, v1.z, v1.w * v1.w);
+          }
+          for (; j < n4; j += g) {
+            const float4 v0 = __ldg(p4 + j);
+            s += (v0.x + v0.y) + (v0.z + v0.w);
+            ss += fmaf(v0.x, v0.x, v0.y * v0.y) + fmaf(v0.z, v0.z, v0.w * v0.w);
+          }
+        } else {
+          for (int j = lj; j < n2; j += g) {
+            const float v = p[j];
+            s += v;
+            ss = fmaf(v, v, ss);
+          }
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = g >> 1; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         ss += __shfl_xor_sync(0xffffffffu, ss, o);
       }
-      if (lane == 0) {
+      if (ok && lj == 0) {
         atomicAdd(&acc[((int64_t)b * C + c) * 2], (double)s);
         atomicAdd(&acc[((int64_t)b * C + c) * 2 + 1], (double)ss);
       }
@@ -174,35 +219,56 @@ __global__ void __launch_bounds__(256) norm_act_split_tr_kernel(const float* __r
                                                                 const float* __restrict__ beta, int act,
                                                                 __nv_bfloat16* __restrict__ planes, int64_t ldp,
                                                                 int64_t p_plane) {
-  __shared__ float tile[32][33];
+  // 32 channels x 64 frequencies per block: channel-contiguous 128-byte loads, frequency-contiguous bf16x2 stores
+  // (128 bytes per warp and plane)
+  __shared__ float tile[32][66];
   const int64_t bt = blockIdx.z;
-  const int f0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int f0 = blockIdx.y * 64, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
   const int64_t b = bt / T;
+  const int c = c0 + tx;
+  float2 st = make_float2(0.f, 1.f);
+  float ga = 1.f, be = 0.f;
+  if (stats != nullptr && c < C) {
+    st = stats[b * C + c];
+    ga = gamma[c];
+    be = beta[c];
+  }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int f = f0 + ty + 8 * k, c = c0 + tx;
+  for (int k = 0; k < 8; ++k) {
+    const int f = f0 + ty + 8 * k;
     float y = 0.f;
     if (f < F && c < C) {
-      y = x[(bt * F + f) * ld + c];
-      if (stats != nullptr) {
-        const float2 st = stats[b * C + c];
-        y = (y - st.x) * st.y * gamma[c] + beta[c];
-      }
+      y = __ldg(x + (bt * F + f) * ld + c);
+      if (stats != nullptr) y = (y - st.x) * st.y * ga + be;
       y = apply_act(y, act);
     }
-    tile[ty + 8 * k][tx] = y;
+    tile[tx][ty + 8 * k] = y;
   }
   __syncthreads();
+  const bool pair_ok = (ldp & 1) == 0 && (p_plane & 1) == 0 && (reinterpret_cast<uintptr_t>(planes) & 3) == 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int c = c0 + ty + 8 * k, f = f0 + tx;
-    if (c < C && f < F) {
-      __nv_bfloat16 h, l;
-      tc::split_bf16(tile[tx][ty + 8 * k], h, l);
-      const int64_t o = (bt * C + c) * ldp + f;
-      planes[o] = h;
-      planes[o + p_plane] = l;
+    const int cc = c0 + ty + 8 * k, f = f0 + 2 * tx;
+    if (cc < C && f < F) {
+      const float2 v = *reinterpret_cast<const float2*>(&tile[ty + 8 * k][2 * tx]);
+      const int64_t o = (bt * C + cc) * ldp + f;
+      if (pair_ok && f + 1 < F) {
+        uint32_t h, l;
+        tc::split_bf16x2(v.x, v.y, h, l);
+        *reinterpret_cast<uint32_t*>(planes + o) = h;
+        *reinterpret_cast<uint32_t*>(planes + o + p_plane) = l;
+      } else {
+        __nv_bfloat16 h, l;
+        tc::split_bf16(v.x, h, l);
+        planes[o] = h;
+        planes[o + p_plane] = l;
+        if (f + 1 < F) {
+          tc::split_bf16(v.y, h, l);
+          planes[o + 1] = h;
+          planes[o + 1 + p_plane] = l;
+        }
+      }
     }
   }
 }
@@ -293,8 +359,15 @@ extern "C" int sesa_instnorm_stats(const float* x, int layout, int batch, int64_
                  "sesa_instnorm_stats: channels-last statistics need channels % 4 == 0 and 16-byte aligned rows");
   cudaStream_t st = (cudaStream_t)stream;
   SESA_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)batch * channels, st));
-  const int64_t chunk = layout == 0 ? 256 : 4;
-  dim3 grid((unsigned)ceil_div64(n1, chunk), batch);
+  // work per block: enough blocks to cover the machine about four times whatever the layer's extent (deep layers have
+  // few positions and many channels), bounded so that fp32 partial sums stay short
+  // layout 0: positions per block; layout 1: rows (position x channel) per block
+  const int64_t units = layout == 0 ? n1 : n1 * channels;
+  int64_t chunk = ceil_div64(units * batch, 148 * 4);
+  const int64_t cmin = layout == 0 ? 8 : 64, cmax = layout == 0 ? 256 : 1024;
+  if (chunk < cmin) chunk = cmin;
+  if (chunk > cmax) chunk = cmax;
+  dim3 grid((unsigned)ceil_div64(units, chunk), batch);
   instnorm_acc_kernel<<<grid, 256, 0, st>>>(x, layout, batch, n1, channels, n2, ld, chunk, scratch);
   SESA_LAUNCH_CHECK();
   const int n = batch * channels;
@@ -316,7 +389,7 @@ extern "C" int sesa_norm_act_split(const float* x, int mode, int batch, int64_t 
     // n1 = T frames, n2 = F: x channels-last [b][t][f][c] -> planes [b][t][c][f]
     const int64_t BT = (int64_t)batch * n1;
     SESA_CHECK_ARG(BT <= 65535, "sesa_norm_act_split: too many (b, t) slices for one launch");
-    dim3 grid((channels + 31) / 32, (n2 + 31) / 32, (unsigned)BT);
+    dim3 grid((channels + 31) / 32, (n2 + 63) / 64, (unsigned)BT);
     norm_act_split_tr_kernel<<<grid, 256, 0, st>>>(x, BT, n2, channels, n1, ld, s2, gamma, beta, act, pl, ldp, p_plane);
   } else {
     const int inner = mode == 0 ? channels : n2;
