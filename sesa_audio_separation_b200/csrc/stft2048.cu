@@ -445,18 +445,11 @@ int sesa_launch_mask_istft2048(const float* spec, const float* mask, const int* 
                                const float* window, const float* env, const float* twiddle, int batch, int nstems,
                                int channels, int hop, int T, int64_t out_len, int mode, int n_gathered,
                                cudaStream_t stream) {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    SESA_CUDA(cudaGetDevice(&dev));
-    SESA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  // frames per CTA: one resident wave (three CTAs per SM) when the launch is small, at most 16; never fewer than
-  // (n_fft - hop) / hop, so that an output sample is shared by at most two CTAs (see the kernel comment)
-  const int g_min = (FN - hop + hop - 1) / hop;
-  int G = (int)ceil_div64((int64_t)T * nstems * batch, (int64_t)sms * 3);
-  if (G > 16) G = 16;
-  if (G < g_min) G = g_min;
+  // frames per CTA: a constant of the transform geometry only — NOT of the batch — so that the grouping of frames, and
+  // with it every rounding, is the same whatever batch a chunk is launched in (batch invariance, sharded == unsharded);
+  // never fewer than (n_fft - hop) / hop, so that an output sample is shared by at most two CTAs (see the kernel comment)
+  const int g_min = (FN - 1) / hop;
+  const int G = g_min > 8 ? g_min : 8;
   const size_t smem = (size_t)2 * FPAD * sizeof(float2) + (size_t)channels * ACC * sizeof(float);
   SESA_CUDA(cudaMemsetAsync(out, 0, (size_t)batch * nstems * channels * out_len * sizeof(float), stream));
 #define SESA_ISTFT_CASE(M, CC)                                                                                       \

@@ -79,6 +79,41 @@ def test_mask_istft_matches_torch(lib, n_fft, hop, C, L, nst):
     assert snr_db(ref.numpy(), out.cpu().numpy()) > 110
 
 
+@pytest.mark.parametrize('B,nst', [(5, 1), (3, 4)])
+def test_stft_and_mask_istft_are_batch_invariant_and_reproducible(lib, B, nst):
+    """A chunk's spectrogram and waveform must not depend on the batch it is launched in (engine batches and chunk-range
+    shards regroup chunks), nor on the arrival order of the iSTFT's two-contributor atomics: bitwise equality of a batched
+    launch, one-by-one launches and a repeated launch, at a frame count that spans many frame groups."""
+    from sesa_audio_separation_b200.roformer import _istft_envelope
+    dev = 'cuda'
+    n_fft, hop, C, L = 2048, 441, 2, 441 * 400
+    T, F = 1 + L // hop, n_fft // 2 + 1
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(B, C, L, device=dev, generator=g)
+    mask = torch.randn(nst, B * T, F * C * 2, device=dev, generator=g)
+    win = torch.hann_window(n_fft)
+    env = _istft_envelope(win, n_fft, hop, T, L).to(dev)
+    wd, tw = win.to(dev), _tw(n_fft, dev)
+    spec = torch.empty(B * T, F, C, 2, device=dev)
+    out = torch.empty(B, nst, C, L, device=dev)
+    lib.call('sesa_stft', P(x), P(spec), P(wd), P(tw), B, C, L, n_fft, hop, 0, F, S())
+    lib.call('sesa_mask_istft', P(spec), P(mask), None, None, P(out), P(wd), P(env), P(tw), B, nst, C, n_fft, hop, T, L, 0, 0, S())
+    out2 = torch.empty_like(out)
+    lib.call('sesa_mask_istft', P(spec), P(mask), None, None, P(out2), P(wd), P(env), P(tw), B, nst, C, n_fft, hop, T, L, 0, 0, S())
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    for b in range(B):
+        sb = torch.empty(T, F, C, 2, device=dev)
+        ob = torch.empty(1, nst, C, L, device=dev)
+        xb = x[b:b + 1].contiguous()
+        mb = mask[:, b * T:(b + 1) * T].contiguous()
+        lib.call('sesa_stft', P(xb), P(sb), P(wd), P(tw), 1, C, L, n_fft, hop, 0, F, S())
+        lib.call('sesa_mask_istft', P(sb), P(mb), None, None, P(ob), P(wd), P(env), P(tw), 1, nst, C, n_fft, hop, T, L, 0, 0, S())
+        torch.cuda.synchronize()
+        assert torch.equal(sb, spec[b * T:(b + 1) * T]), b
+        assert torch.equal(ob[0], out[b]), (b, float((ob[0] - out[b]).abs().max()))
+
+
 def _run_gemm(lib, A, W, bias, Cbuf, ep_kwargs, M, N, K, lda, ldc):
     from sesa_audio_separation_b200.roformer import _GroupTable, _epilogue
     tab = _GroupTable([dict(A=A.data_ptr(), W=W.data_ptr(), bias=bias.data_ptr() if bias is not None else 0,
