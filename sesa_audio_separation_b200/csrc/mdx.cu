@@ -212,6 +212,67 @@ __global__ void __launch_bounds__(256) norm_act_split_kernel(const float* __rest
   }
 }
 
+// Mode 0 fast path (channels-last rows of C = 4 * quads channels, quads a divisor of 256): grid (slices, batch); a thread
+// keeps ONE channel quad for the whole launch, so the (mean, rstd, gamma, beta) of its four channels live in registers and
+// the row loop has no divisions; two rows in flight per thread.
+__global__ void __launch_bounds__(256) norm_act_split_cl_kernel(const float* __restrict__ x, int64_t n1, int C, int64_t ld,
+                                                                int64_t rows_per_block, const float2* __restrict__ stats,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                int act, __nv_bfloat16* __restrict__ planes, int64_t ldp,
+                                                                int64_t p_plane) {
+  const int quads = C >> 2;
+  const int rpp = 256 / quads;                       // rows per pass
+  const int tq = threadIdx.x % quads, tr = threadIdx.x / quads;
+  const int b = blockIdx.y;
+  const int q = 4 * tq;
+  float mean[4] = {0.f, 0.f, 0.f, 0.f}, scale[4] = {1.f, 1.f, 1.f, 1.f}, shift[4] = {0.f, 0.f, 0.f, 0.f};
+  if (stats != nullptr) {
+    const float4 s01 = __ldg(reinterpret_cast<const float4*>(stats + (int64_t)b * C + q));
+    const float4 s23 = __ldg(reinterpret_cast<const float4*>(stats + (int64_t)b * C + q + 2));
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + q));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + q));
+    mean[0] = s01.x; mean[1] = s01.z; mean[2] = s23.x; mean[3] = s23.z;
+    scale[0] = s01.y; scale[1] = s01.w; scale[2] = s23.y; scale[3] = s23.w;
+    shift[0] = b4.x; shift[1] = b4.y; shift[2] = b4.z; shift[3] = b4.w;
+    // keep the reference's evaluation order: ((x - mean) * rstd) * gamma + beta
+    const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
+    auto finish = [&](const float4 v, int64_t r) {
+      float in[4] = {v.x, v.y, v.z, v.w}, o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = apply_act((in[e] - mean[e]) * scale[e] * gm[e] + shift[e], act);
+      uint32_t h0, l0, h1, l1;
+      tc::split_bf16x2(o[0], o[1], h0, l0);
+      tc::split_bf16x2(o[2], o[3], h1, l1);
+      __nv_bfloat16* pr = planes + r * ldp + q;
+      *reinterpret_cast<uint2*>(pr) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(l0, l1);
+    };
+    const int64_t r_begin = (int64_t)b * n1 + (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min((int64_t)(b + 1) * n1, r_begin + rows_per_block);
+    int64_t r = r_begin + tr;
+    for (; r + rpp < r_end; r += 2 * rpp) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(x + r * ld + q));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(x + (r + rpp) * ld + q));
+      finish(v0, r);
+      finish(v1, r + rpp);
+    }
+    if (r < r_end) finish(__ldg(reinterpret_cast<const float4*>(x + r * ld + q)), r);
+    return;
+  }
+  // no statistics: activation + split only
+  const int64_t r_begin = (int64_t)b * n1 + (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min((int64_t)(b + 1) * n1, r_begin + rows_per_block);
+  for (int64_t r = r_begin + tr; r < r_end; r += rpp) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + q));
+    uint32_t h0, l0, h1, l1;
+    tc::split_bf16x2(apply_act(v.x, act), apply_act(v.y, act), h0, l0);
+    tc::split_bf16x2(apply_act(v.z, act), apply_act(v.w, act), h1, l1);
+    __nv_bfloat16* pr = planes + r * ldp + q;
+    *reinterpret_cast<uint2*>(pr) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(l0, l1);
+  }
+}
+
 // mode 1: channels-last x[(bt*F + f)*ld + c] -> channel-major planes[(bt*C + c)*ldp + f]   (TDF input, :117-119)
 __global__ void __launch_bounds__(256) norm_act_split_tr_kernel(const float* __restrict__ x, int64_t BT, int F, int C,
                                                                 int64_t T, int64_t ld, const float2* __restrict__ stats,
@@ -396,6 +457,19 @@ extern "C" int sesa_norm_act_split(const float* x, int mode, int batch, int64_t 
     SESA_CHECK_ARG((inner & 3) == 0 && (ldp & 3) == 0 && (p_plane & 3) == 0 && (mode != 0 || (ld & 3) == 0),
                    "sesa_norm_act_split: inner extent and strides must be multiples of 4");
     const int64_t rows = mode == 0 ? (int64_t)batch * n1 : (int64_t)batch * n1 * channels;
+    const int cq = channels >> 2;
+    if (mode == 0 && cq >= 1 && cq <= 256 && 256 % cq == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        (stats == nullptr || ((reinterpret_cast<uintptr_t>(stats) & 15) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
+                              (reinterpret_cast<uintptr_t>(beta) & 15) == 0)) && batch <= 65535) {
+      // rows per block: about eight blocks per SM over the whole launch, a multiple of the rows a block covers per pass
+      const int rpp = 256 / cq;
+      int64_t rpb = ceil_div64(n1 * batch, 148 * 8);
+      rpb = ceil_div64(rpb, 2 * rpp) * 2 * rpp;
+      dim3 grid((unsigned)ceil_div64(n1, rpb), batch);
+      norm_act_split_cl_kernel<<<grid, 256, 0, st>>>(x, n1, channels, ld, rpb, s2, gamma, beta, act, pl, ldp, p_plane);
+      SESA_LAUNCH_CHECK();
+      return SESA_OK;
+    }
     const int64_t total = rows * (inner >> 2);
     norm_act_split_kernel<<<(unsigned)min((int64_t)148 * 16, ceil_div64(total, 256)), 256, 0, st>>>(
         x, mode, rows, channels, n2, n1, ld, s2, gamma, beta, act, pl, ldp, p_plane);
