@@ -45,6 +45,7 @@ struct AttnParams {
   int tiles_per_group;  //         sequence's arithmetic never depends on the batch it is launched in
   int q_tiles;          // strided: 128-row query tiles per sequence
   int out_planes;
+  int total_work;        // work items (row tiles x heads) of the launch
 };
 
 // 64-thread named barrier of the warp pair (w, w+4) that shares a TMEM lane quadrant (ids 1..4, compile-time ids keep
@@ -67,8 +68,8 @@ struct ACfg {
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NP * Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * NP * KV_BYTES;
-  static constexpr int OFF_X = OFF_V + KV_STAGES * NP * KV_BYTES;   // float xch[2][2][128]: row max / row sum exchange
-  static constexpr int OFF_BAR = OFF_X + 2 * 2 * BQ * 4;
+  static constexpr int OFF_X = OFF_V + KV_STAGES * NP * KV_BYTES;   // float xch[3][2][128]: row max (2 slots) / row sum exchange
+  static constexpr int OFF_BAR = OFF_X + 3 * 2 * BQ * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM columns: SP[0] [0,64) | SP[1] [64,128) | O [128,192).
   // SP[b] holds the fp32 scores of block j (b = j&1) and is overwritten IN PLACE by P (bf16 pairs: hi in the first
@@ -76,6 +77,34 @@ struct ACfg {
   static constexpr int TMEM_COLS = 256;
 };
 
+// work item w -> (head, row tile): heads fastest, so that the CTAs working on the 8 heads of one row tile run together and
+// the 256-byte L2 fetches around each 128-byte head slice are shared instead of being fetched twice from HBM
+struct WorkItem {
+  int h, item, q0, c1, c3;
+  int64_t row_base;
+};
+__device__ __forceinline__ WorkItem decode_work(const AttnParams& p, int w) {
+  WorkItem it;
+  it.h = w % p.heads;
+  it.item = w / p.heads;
+  it.q0 = 0; it.c1 = 0; it.c3 = 0; it.row_base = 0;
+  if (p.mode == 0) {
+    const int seq = it.item / p.q_tiles;
+    it.q0 = (it.item - seq * p.q_tiles) * BQ;
+    it.c1 = seq % p.inner_cnt;
+    it.c3 = seq / p.inner_cnt;
+  } else {
+    const int grp = it.item / p.tiles_per_group;
+    const int lt = it.item - grp * p.tiles_per_group;
+    it.row_base = ((int64_t)grp * p.seq_group + (int64_t)lt * p.spt) * p.seq_len;
+  }
+  return it;
+}
+
+// Persistent CTAs (two per SM): each walks work items w = blockIdx.x, blockIdx.x + gridDim.x, ... and all mbarrier phases run
+// on a block counter g that continues across items, so the Q/K/V loads and the first two score MMAs of item n+1 are issued
+// while the softmax threads finish item n: the tensor pipe does not drain at item boundaries and the barrier / TMEM set-up
+// is paid once per CTA instead of once per tile.
 template <int NSPLIT>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
@@ -87,25 +116,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
   uint8_t* sV = smem + C::OFF_V;
   float* xch = reinterpret_cast<float*>(smem + C::OFF_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2] TMA -> MMA
-  uint64_t* k_empty = bars + 3;   // [2] MMA (commit) -> TMA
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [2] MMA (commit) -> softmax
-  uint64_t* p_full = bars + 11;   // [2] softmax (256 arrivals) -> MMA
-  uint64_t* o_full = bars + 13;   // [2] MMA (commit) -> softmax
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_full = bars + 0;    // TMA -> MMA, once per item
+  uint64_t* q_empty = bars + 1;   // MMA (commit after the item's last S) -> TMA
+  uint64_t* k_full = bars + 2;    // [2] TMA -> MMA
+  uint64_t* k_empty = bars + 4;   // [2] MMA (commit) -> TMA
+  uint64_t* v_full = bars + 6;    // [2]
+  uint64_t* v_empty = bars + 8;   // [2]
+  uint64_t* s_full = bars + 10;   // [2] MMA (commit) -> softmax
+  uint64_t* p_full = bars + 12;   // [2] softmax (256 arrivals) -> MMA
+  uint64_t* o_full = bars + 14;   // [2] MMA (commit) -> softmax
+  uint64_t* o_empty = bars + 16;  // softmax (256 arrivals: O of the item has been read) -> MMA, once per item
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  // flat grid, heads fastest: the CTAs of the 8 heads of one row tile run together, so the 256-byte L2 fetches around
-  // each 128-byte head slice are shared instead of being fetched twice from HBM
-  const int h = blockIdx.x % p.heads;
-  const int item = blockIdx.x / p.heads;
 
   if (tid == SM_THREADS) {
     tc::mbar_init(q_full, 1);
+    tc::mbar_init(q_empty, 1);
+    tc::mbar_init(o_empty, SM_THREADS);
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&k_full[b], 1);
       tc::mbar_init(&k_empty[b], 1);
@@ -128,61 +157,55 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
   const uint32_t tmem_SP = tmem_base;         // + 64*b
   const uint32_t tmem_O = tmem_base + 128;
 
-  // ---- work item geometry
-  int nblk, q0 = 0;
-  int c1 = 0, c3 = 0;          // TMA coordinates that stay fixed (strided: f and b)
-  int64_t row_base = 0;        // packed: first row of the tile
-  if (p.mode == 0) {
-    const int seq = item / p.q_tiles;
-    q0 = (item - seq * p.q_tiles) * BQ;
-    c1 = seq % p.inner_cnt;
-    c3 = seq / p.inner_cnt;
-    nblk = (p.seq_len + BKV - 1) / BKV;
-  } else {
-    const int grp = item / p.tiles_per_group;
-    const int lt = item - grp * p.tiles_per_group;
-    row_base = ((int64_t)grp * p.seq_group + (int64_t)lt * p.spt) * p.seq_len;
-    nblk = BQ / BKV;
-  }
+  const int nblk = p.mode == 0 ? (p.seq_len + BKV - 1) / BKV : BQ / BKV;   // KV blocks per item
+  const int total = p.total_work;
 
   if (warp == 9) {
     // ================= TMA producer =================
     if (tc::elect_one()) {
-      auto load_rows = [&](uint8_t* dst, uint64_t* bar, int col, int r0, int plane) {
-        // 64 rows x 64 columns of one plane (rows beyond the tensor are zero-filled by TMA)
-        if (p.mode == 0) tc::tma_load_5d(dst, &map, bar, col, c1, r0, c3, plane);
-        else tc::tma_load_5d(dst, &map, bar, col, (int)(row_base + r0), 0, 0, plane);
-      };
-      const int colq = h * DH, colk = p.inner + h * DH, colv = 2 * p.inner + h * DH;
-      auto load_k = [&](int j) {
-        const int st = j & 1;
-        tc::mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);   // S_{j-2} retired (passes at once for j < 2)
-        tc::mbar_expect_tx(&k_full[st], C::NP * C::KV_BYTES);
+      uint32_t G = 0;   // block counter of the item's first block
+      int n = 0;        // items done by this CTA
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++n, G += nblk) {
+        const WorkItem it = decode_work(p, w);
+        auto load_rows = [&](uint8_t* dst, uint64_t* bar, int col, int r0, int plane) {
+          // 64 rows x 64 columns of one plane (rows beyond the tensor are zero-filled by TMA)
+          if (p.mode == 0) tc::tma_load_5d(dst, &map, bar, col, it.c1, r0, it.c3, plane);
+          else tc::tma_load_5d(dst, &map, bar, col, (int)(it.row_base + r0), 0, 0, plane);
+        };
+        const int colq = it.h * DH, colk = p.inner + it.h * DH, colv = 2 * p.inner + it.h * DH;
+        auto load_k = [&](int j) {
+          const uint32_t g = G + j;
+          const int st = g & 1;
+          tc::mbar_wait(&k_empty[st], ((g >> 1) & 1) ^ 1);   // S_{g-2} retired (passes at once for g < 2)
+          tc::mbar_expect_tx(&k_full[st], C::NP * C::KV_BYTES);
 #pragma unroll
-        for (int pl = 0; pl < C::NP; ++pl) load_rows(sK + (st * C::NP + pl) * C::KV_BYTES, &k_full[st], colk, j * BKV, pl);
-      };
-      auto load_v = [&](int j) {
-        const int st = j & 1;
-        tc::mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);   // P_{j-2} V_{j-2} retired
-        tc::mbar_expect_tx(&v_full[st], C::NP * C::KV_BYTES);
+          for (int pl = 0; pl < C::NP; ++pl) load_rows(sK + (st * C::NP + pl) * C::KV_BYTES, &k_full[st], colk, j * BKV, pl);
+        };
+        auto load_v = [&](int j) {
+          const uint32_t g = G + j;
+          const int st = g & 1;
+          tc::mbar_wait(&v_empty[st], ((g >> 1) & 1) ^ 1);   // P_{g-2} V_{g-2} retired
+          tc::mbar_expect_tx(&v_full[st], C::NP * C::KV_BYTES);
 #pragma unroll
-        for (int pl = 0; pl < C::NP; ++pl) load_rows(sV + (st * C::NP + pl) * C::KV_BYTES, &v_full[st], colv, j * BKV, pl);
-      };
-      tc::mbar_expect_tx(q_full, C::NP * C::Q_BYTES);
+          for (int pl = 0; pl < C::NP; ++pl) load_rows(sV + (st * C::NP + pl) * C::KV_BYTES, &v_full[st], colv, j * BKV, pl);
+        };
+        if (n > 0) tc::mbar_wait(q_empty, (n - 1) & 1);       // every S of the previous item has read Q
+        tc::mbar_expect_tx(q_full, C::NP * C::Q_BYTES);
 #pragma unroll
-      for (int pl = 0; pl < C::NP; ++pl) {
-        load_rows(sQ + pl * C::Q_BYTES, q_full, colq, q0, pl);
-        load_rows(sQ + pl * C::Q_BYTES + C::KV_BYTES, q_full, colq, q0 + 64, pl);
-      }
-      // issue order follows the order in which the tensor pipe frees the stages:
-      // S_0 S_1 PV_0 S_2 PV_1 S_3 ...  =>  K_0 V_0 K_1 V_1 K_2 | K_3 V_2 | K_4 V_3 | ...
-      load_k(0);
-      load_v(0);
-      if (nblk > 1) { load_k(1); load_v(1); }
-      if (nblk > 2) load_k(2);
-      for (int j = 2; j < nblk; ++j) {
-        if (j + 1 < nblk) load_k(j + 1);
-        load_v(j);
+        for (int pl = 0; pl < C::NP; ++pl) {
+          load_rows(sQ + pl * C::Q_BYTES, q_full, colq, it.q0, pl);
+          load_rows(sQ + pl * C::Q_BYTES + C::KV_BYTES, q_full, colq, it.q0 + 64, pl);
+        }
+        // issue order follows the order in which the tensor pipe frees the stages:
+        // S_0 S_1 PV_0 S_2 PV_1 S_3 ...  =>  K_0 V_0 K_1 V_1 K_2 | K_3 V_2 | K_4 V_3 | ...
+        load_k(0);
+        load_v(0);
+        if (nblk > 1) { load_k(1); load_v(1); }
+        if (nblk > 2) load_k(2);
+        for (int j = 2; j < nblk; ++j) {
+          if (j + 1 < nblk) load_k(j + 1);
+          load_v(j);
+        }
       }
     }
   } else if (warp == 8) {
@@ -191,9 +214,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       constexpr uint32_t idesc_s = tc::make_idesc_bf16(BQ, BKV, 0, 0);  // S = Q K^T : both K-major
       constexpr uint32_t idesc_o = tc::make_idesc_bf16(BQ, DH, 0, 1);   // O = P V   : P from TMEM, V MN-major
       const uint32_t aQ = tc::smem_u32(sQ), aK = tc::smem_u32(sK), aV = tc::smem_u32(sV);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        tc::mbar_wait(&k_full[st], (j >> 1) & 1);
+      // The CTA's blocks are numbered g = 0, 1, ... across its items (item n = g / nblk, in-item index j = g % nblk).  The
+      // tensor pipe runs S_0 S_1 | PV_0 S_2 | PV_1 S_3 | ...: scores run two blocks ahead of P V, also across item
+      // boundaries (nblk may be 1).
+      const int n_items = blockIdx.x < total ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const uint32_t GB = (uint32_t)n_items * (uint32_t)nblk;
+      auto issue_s = [&](uint32_t g) {
+        const int n = (int)(g / (uint32_t)nblk);
+        const int j = (int)(g - (uint32_t)n * (uint32_t)nblk);
+        const int st = g & 1;
+        if (j == 0) tc::mbar_wait(q_full, n & 1);
+        tc::mbar_wait(&k_full[st], (g >> 1) & 1);
         tc::tc_fence_after();
 #pragma unroll
         for (int prod = 0; prod < NSPLIT; ++prod) {
@@ -206,15 +237,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
         }
         tc::umma_commit(&s_full[st]);
         tc::umma_commit(&k_empty[st]);
+        if (j == nblk - 1) tc::umma_commit(q_empty);   // Q may be overwritten once these MMAs retire
       };
-      tc::mbar_wait(q_full, 0);
-      issue_s(0);
-      if (nblk > 1) issue_s(1);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        tc::mbar_wait(&p_full[st], ph);       // P_j is in TMEM (S_j consumed); any rescale of O is complete
+      if (GB > 0) issue_s(0);
+      if (GB > 1) issue_s(1);
+      int n = 0, j = 0;
+      for (uint32_t g = 0; g < GB; ++g) {
+        const int st = g & 1;
+        const uint32_t ph = (g >> 1) & 1;
+        tc::mbar_wait(&p_full[st], ph);       // P_g is in TMEM (S_g consumed); any rescale of O is complete
         tc::mbar_wait(&v_full[st], ph);
+        if (j == 0 && n > 0) tc::mbar_wait(o_empty, (n - 1) & 1);   // the previous item's O tile has been read
         tc::tc_fence_after();
 #pragma unroll
         for (int prod = 0; prod < NSPLIT; ++prod) {
@@ -227,134 +260,150 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
         }
         tc::umma_commit(&o_full[st]);
         tc::umma_commit(&v_empty[st]);
-        if (j + 2 < nblk) issue_s(j + 2);     // overwrites SP[st] after P_j V_j (the tensor pipe runs in issue order)
+        // scores two blocks ahead overwrite SP[st] after P_g V_g (the tensor pipe runs in issue order)
+        if (g + 2 < GB) issue_s(g + 2);
+        if (++j == nblk) { j = 0; ++n; }
       }
     }
   } else {
-    // ================= softmax / accumulate threads =================
+    // ================= softmax threads =================
     // Two threads per query row: thread (row i, half hf) owns keys [32 hf, 32 hf + 32) of every 64-key block and
     // output dims [32 hf, 32 hf + 32).  The row maximum is agreed through shared memory once per block.  O accumulates in
     // tensor memory; the threads touch it only to rescale (rare) and to read the finished tile.
     const int hf = warp >> 2;
     const int i = (warp & 3) * 32 + (tid & 31);   // row of the tile == TMEM lane
-    int lo = 0, hi = p.seq_len;                   // valid key range (tile-relative key index)
-    bool row_valid;
-    int64_t out_row;
-    if (p.mode == 0) {
-      row_valid = q0 + i < p.seq_len;
-      out_row = (int64_t)c3 * p.outer_stride + (int64_t)c1 * p.inner_stride + (int64_t)(q0 + i) * p.pos_stride;
-    } else {
-      const int sl = i / p.seq_len;
-      const int grp = item / p.tiles_per_group;
-      const int lseq = (item - grp * p.tiles_per_group) * p.spt + sl;   // sequence index inside its group
-      row_valid = sl < p.spt && lseq < p.seq_group && (int64_t)grp * p.seq_group + lseq < p.n_seq;
-      lo = row_valid ? sl * p.seq_len : 0;
-      hi = row_valid ? lo + p.seq_len : 0;
-      out_row = row_base + i;
-    }
-    // the gate logit of this (row, head) is only needed at the very end: request it now so its latency is never exposed
-    const float gl = row_valid ? __ldg(p.gates + out_row * p.ldg + h) : 0.f;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     constexpr int HC = BKV / 2;   // 32 score columns / output dims per thread
-    float mref = -INFINITY, lrun = 0.f;   // exponent reference of the row (lags the true maximum by at most 2^8), row sum
-    // a warp whose 32 rows all lie beyond the sequence (the last query tile of 801 = 6 x 128 + 33 rows) only keeps the
-    // barrier protocol going: its P rows are never stored, so their content does not matter
-    const bool warp_active = __any_sync(0xffffffffu, row_valid);
-
-    for (int j = 0; j < nblk; ++j) {
-      const int st = j & 1;
-      tc::mbar_wait(&s_full[st], (j >> 1) & 1);
-      if (!warp_active) {
-        tc::mbar_arrive(&p_full[st]);
-        continue;
-      }
-      tc::tc_fence_after();
-      float s[HC];
-      tc::tmem_ld32(tmem_SP + st * 64 + lane_off + hf * HC, s);
-      tc::tmem_ld_wait();
-      const int k0 = j * BKV + hf * HC;
-      float mx = -INFINITY;     // row maximum of the RAW scores; the log2(e) factor is folded into the exp2 argument FMA
-      if (__all_sync(0xffffffffu, k0 >= lo && k0 + HC <= hi)) {
-#pragma unroll
-        for (int c = 0; c < HC; ++c) mx = fmaxf(mx, s[c]);
+    uint32_t G = 0;
+    int n = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++n, G += nblk) {
+      const WorkItem it = decode_work(p, w);
+      int lo = 0, hi = p.seq_len;                   // valid key range (tile-relative key index)
+      bool row_valid;
+      int64_t out_row;
+      if (p.mode == 0) {
+        row_valid = it.q0 + i < p.seq_len;
+        out_row = (int64_t)it.c3 * p.outer_stride + (int64_t)it.c1 * p.inner_stride + (int64_t)(it.q0 + i) * p.pos_stride;
       } else {
-#pragma unroll
-        for (int c = 0; c < HC; ++c) {
-          const int kj = k0 + c;
-          s[c] = (kj >= lo && kj < hi) ? s[c] : -INFINITY;
-          mx = fmaxf(mx, s[c]);
-        }
+        const int sl = i / p.seq_len;
+        const int grp = it.item / p.tiles_per_group;
+        const int lseq = (it.item - grp * p.tiles_per_group) * p.spt + sl;   // sequence index inside its group
+        row_valid = sl < p.spt && lseq < p.seq_group && (int64_t)grp * p.seq_group + lseq < p.n_seq;
+        lo = row_valid ? sl * p.seq_len : 0;
+        hi = row_valid ? lo + p.seq_len : 0;
+        out_row = it.row_base + i;
       }
-      float* xm = xch + (st * 2) * BQ;
-      xm[hf * BQ + i] = mx;
-      tc::tc_fence_before();
-      // the two threads of a row sit in warps w and w+4: a 64-thread named barrier per warp pair (also orders
-      // "both halves of every row have read their scores" before P overwrites them in place)
-      pair_barrier(warp & 3);
-      tc::tc_fence_after();
-      const float mnew = fmaxf(mref, fmaxf(mx, xm[(hf ^ 1) * BQ + i]));
-      // lazy rescaling: keep the old reference while exp2 arguments stay below 8 (p < 256: harmless for the bf16 split
-      // and the fp32 accumulators).  Both threads of a row take the same decision from the same numbers.
-      const bool grow = (mnew - mref) * LOG2E > 8.0f;   // also true for the first finite maximum (mref = -inf)
-      if (__any_sync(0xffffffffu, grow)) {
-        const float corr = grow ? tc::ex2_approx((mref - mnew) * LOG2E) : 1.0f;   // exp2(-inf) = 0 on the first block
-        if (j > 0) {
-          // rows of this warp moved their reference: rescale our 32 columns of O once every earlier P V has retired
-          tc::mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          tc::tc_fence_after();
-          float ob[HC];
-          tc::tmem_ld32(tmem_O + lane_off + hf * HC, ob);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int d = 0; d < HC; ++d) ob[d] *= corr;
-          tc::tmem_st32(tmem_O + lane_off + hf * HC, reinterpret_cast<const uint32_t*>(ob));
-        }
-        lrun *= corr;
-        if (grow) mref = mnew;
-      }
-      const float moff = (mref == -INFINITY ? 0.f : mref) * LOG2E;
-      float sum = 0.f;
-      uint32_t phi[HC / 2], plo[HC / 2];
-#pragma unroll
-      for (int e = 0; e < HC / 2; ++e) {
-        const float p0 = tc::ex2_approx(fmaf(s[2 * e], LOG2E, -moff));
-        const float p1 = tc::ex2_approx(fmaf(s[2 * e + 1], LOG2E, -moff));
-        sum += p0 + p1;
-        tc::split_bf16x2(p0, p1, phi[e], plo[e]);
-      }
-      tc::tmem_st16(tmem_SP + st * 64 + lane_off + hf * (HC / 2), phi);
-      if (NSPLIT == 3) tc::tmem_st16(tmem_SP + st * 64 + lane_off + 32 + hf * (HC / 2), plo);
-      tc::tmem_st_wait();
-      lrun += sum;
-      tc::tc_fence_before();
-      tc::mbar_arrive(&p_full[st]);
-    }
-    // the finished O tile
-    float o[HC];
-    if (warp_active) {
-    tc::mbar_wait(&o_full[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
-    tc::tc_fence_after();
-    tc::tmem_ld32(tmem_O + lane_off + hf * HC, o);
-    tc::tmem_ld_wait();
-    tc::tc_fence_before();
-    }
+      // the gate logit of this (row, head) is only needed at the very end: request it now so its latency is never exposed
+      const float gl = row_valid ? __ldg(p.gates + out_row * p.ldg + it.h) : 0.f;
+      float mref = -INFINITY, lrun = 0.f;   // exponent reference of the row (lags the true maximum by at most 2^8), row sum
+      // a warp whose 32 rows all lie beyond the sequence (the last query tile of 801 = 6 x 128 + 33 rows) only keeps the
+      // barrier protocol going: its P rows are never stored, so their content does not matter
+      const bool warp_active = __any_sync(0xffffffffu, row_valid);
 
-    // combine the two halves' row sums, gate, split to planes, store this thread's 32 output dims
-    float* xs = xch + ((nblk & 1) * 2) * BQ;
-    xs[hf * BQ + i] = lrun;
-    pair_barrier(warp & 3);
-    const float ltot = lrun + xs[(hf ^ 1) * BQ + i];
-    if (row_valid) {
-      const float sc = (1.0f / (1.0f + expf(-gl))) / ltot;
-      __nv_bfloat16* op = p.out + out_row * p.ldo + h * DH + hf * HC;
+      for (int j = 0; j < nblk; ++j) {
+        const uint32_t g = G + j;
+        const int st = g & 1;
+        tc::mbar_wait(&s_full[st], (g >> 1) & 1);
+        if (!warp_active) {
+          tc::mbar_arrive(&p_full[st]);
+          continue;
+        }
+        tc::tc_fence_after();
+        float s[HC];
+        tc::tmem_ld32(tmem_SP + st * 64 + lane_off + hf * HC, s);
+        tc::tmem_ld_wait();
+        const int k0 = j * BKV + hf * HC;
+        float mx = -INFINITY;     // row maximum of the RAW scores; the log2(e) factor is folded into the exp2 argument FMA
+        if (__all_sync(0xffffffffu, k0 >= lo && k0 + HC <= hi)) {
 #pragma unroll
-      for (int d8 = 0; d8 < HC / 8; ++d8) {
-        uint32_t hh[4], ll[4];
+          for (int c = 0; c < HC; ++c) mx = fmaxf(mx, s[c]);
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) tc::split_bf16x2(o[d8 * 8 + 2 * e] * sc, o[d8 * 8 + 2 * e + 1] * sc, hh[e], ll[e]);
-        *reinterpret_cast<uint4*>(op + d8 * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-        if (p.out_planes > 1) *reinterpret_cast<uint4*>(op + p.out_plane + d8 * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          for (int c = 0; c < HC; ++c) {
+            const int kj = k0 + c;
+            s[c] = (kj >= lo && kj < hi) ? s[c] : -INFINITY;
+            mx = fmaxf(mx, s[c]);
+          }
+        }
+        float* xm = xch + (st * 2) * BQ;
+        xm[hf * BQ + i] = mx;
+        tc::tc_fence_before();
+        // the two threads of a row sit in warps w and w+4: a 64-thread named barrier per warp pair (also orders
+        // "both halves of every row have read their scores" before P overwrites them in place)
+        pair_barrier(warp & 3);
+        tc::tc_fence_after();
+        const float mnew = fmaxf(mref, fmaxf(mx, xm[(hf ^ 1) * BQ + i]));
+        // lazy rescaling: keep the old reference while exp2 arguments stay below 8 (p < 256: harmless for the bf16 split
+        // and the fp32 accumulators).  Both threads of a row take the same decision from the same numbers.
+        const bool grow = (mnew - mref) * LOG2E > 8.0f;   // also true for the first finite maximum (mref = -inf)
+        if (__any_sync(0xffffffffu, grow)) {
+          const float corr = grow ? tc::ex2_approx((mref - mnew) * LOG2E) : 1.0f;   // exp2(-inf) = 0 on the first block
+          if (j > 0) {
+            // rows of this warp moved their reference: rescale our 32 columns of O once every earlier P V has retired
+            tc::mbar_wait(&o_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            tc::tc_fence_after();
+            float ob[HC];
+            tc::tmem_ld32(tmem_O + lane_off + hf * HC, ob);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < HC; ++d) ob[d] *= corr;
+            tc::tmem_st32(tmem_O + lane_off + hf * HC, reinterpret_cast<const uint32_t*>(ob));
+          }
+          lrun *= corr;
+          if (grow) mref = mnew;
+        }
+        const float moff = (mref == -INFINITY ? 0.f : mref) * LOG2E;
+        float sum = 0.f;
+        // P leaves for tensor memory in two halves of 16 keys (8 packed registers per plane): keeps the live registers of
+        // the loop under the 96 the two-CTA residency allows
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t phi[HC / 4], plo[HC / 4];
+#pragma unroll
+          for (int e = 0; e < HC / 4; ++e) {
+            const float p0 = tc::ex2_approx(fmaf(s[hh * (HC / 2) + 2 * e], LOG2E, -moff));
+            const float p1 = tc::ex2_approx(fmaf(s[hh * (HC / 2) + 2 * e + 1], LOG2E, -moff));
+            sum += p0 + p1;
+            tc::split_bf16x2(p0, p1, phi[e], plo[e]);
+          }
+          tc::tmem_st8(tmem_SP + st * 64 + lane_off + hf * (HC / 2) + hh * (HC / 4), phi);
+          if (NSPLIT == 3) tc::tmem_st8(tmem_SP + st * 64 + lane_off + 32 + hf * (HC / 2) + hh * (HC / 4), plo);
+        }
+        tc::tmem_st_wait();
+        lrun += sum;
+        tc::tc_fence_before();
+        tc::mbar_arrive(&p_full[st]);
       }
+      // the finished O tile (every warp waits for the last P V, so that no thread can run a whole item ahead of o_empty)
+      const uint32_t gl_last = G + nblk - 1;
+      float o[HC];
+      tc::mbar_wait(&o_full[gl_last & 1], (gl_last >> 1) & 1);
+      tc::tc_fence_after();
+      tc::tmem_ld32(tmem_O + lane_off + hf * HC, o);   // unconditional: a conditionally written o[] would stay live
+      tc::tmem_ld_wait();                              // across the whole item loop (32 registers)
+      tc::tc_fence_before();
+      tc::mbar_arrive(o_empty);     // the next item's first P V may overwrite O
+
+      // combine the two halves' row sums (own exchange slot: slots 0/1 belong to the per-block row maxima), gate, split to
+      // planes, store this thread's 32 output dims
+      float* xs = xch + 4 * BQ;
+      xs[hf * BQ + i] = lrun;
+      pair_barrier(warp & 3);
+      const float ltot = lrun + xs[(hf ^ 1) * BQ + i];
+      if (row_valid) {
+        const float sc = (1.0f / (1.0f + expf(-gl))) / ltot;
+        __nv_bfloat16* op = p.out + out_row * p.ldo + it.h * DH + hf * HC;
+#pragma unroll
+        for (int d8 = 0; d8 < HC / 8; ++d8) {
+          uint32_t hh[4], ll[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tc::split_bf16x2(o[d8 * 8 + 2 * e] * sc, o[d8 * 8 + 2 * e + 1] * sc, hh[e], ll[e]);
+          *reinterpret_cast<uint4*>(op + d8 * 8) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          if (p.out_planes > 1) *reinterpret_cast<uint4*>(op + p.out_plane + d8 * 8) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        }
+      }
+      // the slot is rewritten by the next item's exchange only after its own pair barrier sequence: every reader of this
+      // item's sums has passed the barrier above and at least one more (per-block) barrier by then
     }
   }
 
@@ -364,13 +413,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
 }
 
 template <int NSPLIT>
-int launch_attention_tc(const CUtensorMap& map, const AttnParams& p, dim3 grid, cudaStream_t stream) {
+int launch_attention_tc(const CUtensorMap& map, const AttnParams& p, cudaStream_t stream) {
   using C = ACfg<NSPLIT>;
   static bool configured = false;
+  static int sms = 0;
   if (!configured) {
     SESA_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    int dev = 0;
+    SESA_CUDA(cudaGetDevice(&dev));
+    SESA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
+  const int resident = 2 * sms;   // persistent CTAs: two per SM (TMEM 2 x 256 columns, ~97 KB of shared memory each)
+  const unsigned grid = (unsigned)(p.total_work < resident ? p.total_work : resident);
   attention_tc_kernel<NSPLIT><<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(map, p);
   SESA_LAUNCH_CHECK();
   return SESA_OK;
@@ -413,7 +468,6 @@ extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t pla
   p.tiles_per_group = 1;
   p.q_tiles = 1;
   CUtensorMap map;
-  dim3 grid;
   const bool packed = pos_stride == 1 && seq_len <= BKV && inner_cnt == 1 && outer_stride == seq_len;
   const uint32_t box[5] = {64, 1, 64, 1, 1};
   if (packed) {
@@ -429,7 +483,8 @@ extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t pla
     const uint32_t boxp[5] = {64, 64, 1, 1, 1};
     int rc = sesa_make_tmap_bf16(&map, qkv_planes, 5, dims, str, boxp);
     if (rc != SESA_OK) return rc;
-    grid = dim3((unsigned)((int64_t)(n_seq / p.seq_group) * p.tiles_per_group * heads), 1, 1);
+    SESA_CHECK_ARG((int64_t)(n_seq / p.seq_group) * p.tiles_per_group * heads < (1LL << 31), "sesa_attention_tc: too many tiles for one launch");
+    p.total_work = (int)((int64_t)(n_seq / p.seq_group) * p.tiles_per_group * heads);
   } else {
     // sequence s = (b, f): row = b*outer + f*inner + pos*pos_stride
     p.mode = 0;
@@ -442,8 +497,8 @@ extern "C" int sesa_attention_tc(const void* qkv_planes, int64_t ld, int64_t pla
     if (rc != SESA_OK) return rc;
     p.q_tiles = (seq_len + BQ - 1) / BQ;
     SESA_CHECK_ARG((int64_t)n_seq * p.q_tiles * heads < (1LL << 31), "sesa_attention_tc: too many tiles for one launch");
-    grid = dim3((unsigned)((int64_t)n_seq * p.q_tiles * heads), 1, 1);
+    p.total_work = (int)((int64_t)n_seq * p.q_tiles * heads);
   }
-  if (nsplit == 3) return launch_attention_tc<3>(map, p, grid, (cudaStream_t)stream);
-  return launch_attention_tc<1>(map, p, grid, (cudaStream_t)stream);
+  if (nsplit == 3) return launch_attention_tc<3>(map, p, (cudaStream_t)stream);
+  return launch_attention_tc<1>(map, p, (cudaStream_t)stream);
 }

@@ -384,7 +384,10 @@ def test_prep_rows(lib):
 
 @pytest.mark.parametrize('nsplit', [3, 1])
 @pytest.mark.parametrize('axis,B,T,F', [(0, 2, 150, 20), (1, 2, 150, 20), (0, 1, 801, 3), (1, 3, 33, 62), (1, 1, 5, 60),
-                                        (1, 2, 7, 100), (0, 1, 64, 2)])
+                                        (1, 2, 7, 100), (0, 1, 64, 2),
+                                        # more work items than resident CTAs (persistent kernel walks several items per
+                                        # CTA), with one, three and four KV blocks per item, and packed tiles
+                                        (0, 2, 41, 62), (0, 4, 200, 40), (0, 2, 130, 70), (1, 40, 62, 20)])
 def test_attention_tc(lib, axis, B, T, F, nsplit):
     from sesa_audio_separation_b200 import tc
     dev = 'cuda'
