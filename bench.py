@@ -166,6 +166,7 @@ def main():
     ap.add_argument('--seconds', type=float, default=180.0)
     ap.add_argument('--engine-batch', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-rates', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -262,10 +263,8 @@ def main():
         gemm_cls = 'gemm_tc' if tc_mode else 'gemm_simt'
         gemm_n, gemm_ms = prof.get(gemm_cls, (0, 0.0))
         breakdown = {k: {'launches': n, 'ms': round(t, 3)} for k, (n, t) in sorted(prof.items())}
-        # the tensor-core class runs every GEMM except the (tiny) band-split Linears
-        fpb = (2,) * 24 + (4,) * 12 + (12,) * 8 + (24,) * 8 + (48,) * 8 + (128, 129)
-        band_f = 2 * (1 + CHUNK // MODEL_CFG['stft_hop_length']) * sum(4 * f for f in fpb) * MODEL_CFG['dim']
-        cls_f = gemm_f - band_f if tc_mode else gemm_f
+        # the tensor-core class runs every GEMM of the forward, the band-split Linears included
+        cls_f = gemm_f
         achieved = (cls_f * n_chunks / 1e12) / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
         mma_mult = 3 if args.precision == 'fp32' else 1
         traffic = None
@@ -297,6 +296,17 @@ def main():
             'breakdown_ms_per_step': breakdown, 'attention_tflop_per_chunk': att_f / 1e12,
             'kernels': secondary_rooflines(prof, n_chunks, att_f, tf_peak, hbm_peak, args.seconds, mma_mult),
         }
+        if world == 1 and tc_mode and not args.no_kernel_rates:
+            # the HBM-bound kernels again, each alone at the 4-chunk launch shape with L2 flushed between repetitions: the
+            # per-launch event timing of the profiling pass above carries ~10 us of bracketing per launch, which matters
+            # for 10-100 us kernels
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            import hbm_bench
+            iso = hbm_bench.measure(chunks=args.engine_batch, reps=5, seconds=args.seconds)
+            for k, v in iso.items():
+                line['kernels'].setdefault(k, {'bound': 'hbm', 'peak': hbm_peak, 'unit': 'GB/s'})
+                line['kernels'][k].update({'isolated_us_per_launch': round(v['us'], 1), 'isolated_achieved': v['gbs'],
+                                           'isolated_frac': v['gbs'] / hbm_peak})
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(model.state_dict(), 1, 0)
             line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}

@@ -37,19 +37,13 @@ def timed(fn, reps, flush):
     return ms[len(ms) // 2]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--chunks', type=int, default=4)
-    ap.add_argument('--reps', type=int, default=7)
-    ap.add_argument('--stems', type=int, default=1)
-    ap.add_argument('--seconds', type=float, default=180.0)
-    ap.add_argument('--only', default='')
-    args = ap.parse_args()
+def measure(chunks=4, reps=7, stems=1, seconds=180.0, only='', verbose=False):
+    """-> {kernel: {'us', 'bytes', 'gbs', 'frac'}} for stft / mask_istft / overlap_add / framing."""
     _lib.require_cuda()
     _lib.load()
     dev = 'cuda'
     S = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    B, C, L, N, hop, NS = args.chunks, 2, 352800, 2048, 441, args.stems
+    B, C, L, N, hop, NS = chunks, 2, 352800, 2048, 441, stems
     T, F = 1 + L // hop, N // 2 + 1
     g = torch.Generator(device=dev).manual_seed(0)
     flush = torch.empty(128 * 1024 * 1024, device=dev)
@@ -61,43 +55,58 @@ def main():
     mask = torch.randn(NS, B * T, F * C * 2, device=dev, generator=g)
     out = torch.empty(B, NS, C, L, device=dev)
     res = {}
+    sel = set(only.split(',')) if only else None
 
     def report(name, ms, nbytes):
         gbs = nbytes / 1e9 / (ms / 1e3)
-        res[name] = gbs
-        print(f'{name:12s} {ms * 1e3:9.1f} us  {nbytes / 1e6:9.1f} MB  {gbs:8.1f} GB/s  {gbs / HBM_PEAK * 100:5.1f} % of {HBM_PEAK:.0f}', flush=True)
+        res[name] = {'us': ms * 1e3, 'bytes': nbytes, 'gbs': gbs, 'frac': gbs / HBM_PEAK}
+        if verbose:
+            print(f'{name:12s} {ms * 1e3:9.1f} us  {nbytes / 1e6:9.1f} MB  {gbs:8.1f} GB/s  {gbs / HBM_PEAK * 100:5.1f} % of {HBM_PEAK:.0f}', flush=True)
 
-    if not args.only or 'stft' in args.only.split(','):
-        ms = timed(lambda: _lib.call('sesa_stft', P(audio), P(spec), P(win), P(tw), B, C, L, N, hop, 0, F, S), args.reps, flush)
+    if sel is None or 'stft' in sel:
+        ms = timed(lambda: _lib.call('sesa_stft', P(audio), P(spec), P(win), P(tw), B, C, L, N, hop, 0, F, S), reps, flush)
         report('stft', ms, B * (4 * C * L + 8 * C * F * T))
     else:
         _lib.call('sesa_stft', P(audio), P(spec), P(win), P(tw), B, C, L, N, hop, 0, F, S)
-    if not args.only or 'istft' in args.only.split(','):
+    if sel is None or 'istft' in sel:
         ms = timed(lambda: _lib.call('sesa_mask_istft', P(spec), P(mask), None, None, P(out), P(win), P(env), P(tw), B, NS, C, N,
-                                    hop, T, L, 0, 0, S), args.reps, flush)
+                                     hop, T, L, 0, 0, S), reps, flush)
         report('mask_istft', ms, B * (8 * C * F * T + NS * (8 * C * F * T + 4 * C * L)))
     # demix overlap-add over a whole track
-    length = int(args.seconds * 44100)
+    length = int(seconds * 44100)
     plan = make_plan(length, L, 4, 1)
     starts = torch.tensor(plan.starts, dtype=torch.int64).to(dev)
     lens = torch.tensor(plan.lens, dtype=torch.int64).to(dev)
     modes = torch.tensor(plan.modes, dtype=torch.int32).to(dev)
     kinds = torch.tensor(plan.kinds, dtype=torch.int32).to(dev)
-    if not args.only or 'ola' in args.only.split(','):
+    if sel is None or 'ola' in sel:
         chunk_out = torch.randn(plan.n_chunks, NS, C, L, device=dev, generator=g)
         result = torch.empty(NS, C, length, device=dev)
         window = windowing_array(L, plan.fade).to(dev)
         crop = plan.border if plan.pad else 0
         ms = timed(lambda: _lib.call('sesa_overlap_add', P(chunk_out), P(starts), P(lens), P(kinds), plan.n_chunks, plan.step, L,
-                                    plan.fade, P(window), NS, C, plan.padded, crop, length, P(result), None, S), args.reps, flush)
+                                     plan.fade, P(window), NS, C, plan.padded, crop, length, P(result), None, S), reps, flush)
         report('overlap_add', ms, 4 * NS * C * (L * plan.n_chunks + length))
-    if not args.only or 'frame' in args.only.split(','):
+        del chunk_out, result
+    if sel is None or 'frame' in sel:
         padded = torch.randn(C, plan.padded, device=dev, generator=g)
-        chunks = torch.empty(B, C, L, device=dev)
-        ms = timed(lambda: _lib.call('sesa_frame_chunks', P(padded), plan.padded, C, P(starts), P(lens), P(modes), B, L, P(chunks),
-                                    S), args.reps, flush)
+        chunks_t = torch.empty(B, C, L, device=dev)
+        ms = timed(lambda: _lib.call('sesa_frame_chunks', P(padded), plan.padded, C, P(starts), P(lens), P(modes), B, L,
+                                     P(chunks_t), S), reps, flush)
         report('framing', ms, 2 * 4 * B * C * L)
     torch.cuda.synchronize()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--chunks', type=int, default=4)
+    ap.add_argument('--reps', type=int, default=7)
+    ap.add_argument('--stems', type=int, default=1)
+    ap.add_argument('--seconds', type=float, default=180.0)
+    ap.add_argument('--only', default='')
+    args = ap.parse_args()
+    measure(args.chunks, args.reps, args.stems, args.seconds, args.only, verbose=True)
 
 
 if __name__ == '__main__':
