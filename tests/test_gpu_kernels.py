@@ -114,6 +114,33 @@ def test_stft_and_mask_istft_are_batch_invariant_and_reproducible(lib, B, nst):
         assert torch.equal(ob[0], out[b]), (b, float((ob[0] - out[b]).abs().max()))
 
 
+@pytest.mark.parametrize('hop,C', [(441, 2), (512, 2), (441, 1)])
+def test_full_size_stft_istft_round_trip(lib, hop, C):
+    """Size-independent property at the BASELINE chunk size (352 800 samples, n_fft 2048): STFT followed by the fused
+    mask + iSTFT with a unit mask reconstructs the chunk (windowed overlap-add with the exact envelope is the identity),
+    reflect-padded edges included."""
+    from sesa_audio_separation_b200.roformer import _istft_envelope
+    dev = 'cuda'
+    n_fft, L, B = 2048, 352800, 2
+    T, F = 1 + L // hop, n_fft // 2 + 1
+    out_len = min(L, hop * (T - 1))        # samples covered by whole hops (L itself when hop divides L)
+    g = torch.Generator(device=dev).manual_seed(11)
+    x = torch.randn(B, C, L, device=dev, generator=g)
+    win = torch.hann_window(n_fft)
+    env = _istft_envelope(win, n_fft, hop, T, out_len).to(dev)
+    wd, tw = win.to(dev), _tw(n_fft, dev)
+    spec = torch.empty(B * T, F, C, 2, device=dev)
+    mask = torch.zeros(1, B * T, F, C, 2, device=dev)
+    mask[..., 0] = 1.0
+    out = torch.empty(B, 1, C, out_len, device=dev)
+    lib.call('sesa_stft', P(x), P(spec), P(wd), P(tw), B, C, L, n_fft, hop, 0, F, S())
+    lib.call('sesa_mask_istft', P(spec), P(mask), None, None, P(out), P(wd), P(env), P(tw), B, 1, C, n_fft, hop, T, out_len, 0, 0, S())
+    torch.cuda.synchronize()
+    err = float((out[:, 0] - x[..., :out_len]).abs().max())
+    print('round trip hop', hop, 'C', C, 'max abs err', err)
+    assert err < 5e-6        # |x| reaches ~5: a few fp32 ulps through two 2048-point transforms
+
+
 def _run_gemm(lib, A, W, bias, Cbuf, ep_kwargs, M, N, K, lda, ldc):
     from sesa_audio_separation_b200.roformer import _GroupTable, _epilogue
     tab = _GroupTable([dict(A=A.data_ptr(), W=W.data_ptr(), bias=bias.data_ptr() if bias is not None else 0,
