@@ -37,6 +37,7 @@ constexpr int MAX_GROUPS = 1024;
 struct alignas(128) TcGroup {
   CUtensorMap mapA;  // dims (K, M, planes), box (64, 128, 1)
   CUtensorMap mapW;  // dims (K, N, planes), box (64, BN, 1)
+  CUtensorMap mapP;  // output planes, dims (columns, M, planes), box (16, 32, 1), unswizzled: the epilogue's TMA stores
   const float* bias;
   const float* rowscale;
   float* C;
@@ -55,6 +56,7 @@ struct alignas(128) TcGroup {
   int32_t p_cols;       // planes are written for columns < p_cols (0 = all)
   int32_t c_col0;       // C is written for columns >= c_col0, at column n - c_col0
   int32_t ss_ld;        // floats between consecutive rows of ss_out (>= slots; lets band-sliced launches interleave)
+  int32_t p_tma;        // mapP is valid (aligned, unscattered output planes)
 };
 static_assert(sizeof(TcGroup) % 128 == 0, "table entries must keep the tensor maps 128-byte aligned");
 
@@ -335,7 +337,8 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     int as = 0;
     uint32_t aph = 0;
     for (int tile = unit; tile < total_tiles; tile += n_units) {
-      const TcGroup* g = n_groups == 1 ? g_local : &groups[find_group(tile_end, n_groups, tile)];
+      const int gi = n_groups == 1 ? 0 : find_group(tile_end, n_groups, tile);
+      const TcGroup* g = n_groups == 1 ? g_local : &groups[gi];
       const int t = tile - g->tile_begin;
       const int mb = (t / g->n_blocks) * CG + cta_rank, nb = t % g->n_blocks;
       const int M = g->M, N = g->N;
@@ -349,6 +352,107 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       const int p_cols = g->p_cols > 0 ? g->p_cols : (use_glu ? N >> 1 : N);
       const int c_col0 = g->c_col0;
       const int row_map = g->row_map, rm_F = g->rm_F, rm_dt = g->rm_dt, rm_df = g->rm_df;
+      // ---------------------------------------------------------------------------------------------------------------
+      // Row-owner path (planes-only outputs: ff1, to_qkv, MaskEstimator hidden layers): the thread that reads an
+      // accumulator row from TMEM finishes it — row scale and sequence position are per-thread scalars, bias comes as
+      // broadcast ld.shared, no transpose, no per-row address arithmetic or predicates — and leaves the bf16 planes in
+      // shared memory as dense [32 rows][16 columns] boxes that one lane hands to TMA (cp.async.bulk.tensor store, rows
+      // beyond M clipped by the tensor map).
+      constexpr bool kRowOwnerFlavor = FLAVOR == F_GELU || FLAVOR == F_ROT || FLAVOR == F_TANH;
+      const bool row_owner = kRowOwnerFlavor && g->p_tma != 0 && Pp != nullptr && row_map == 0 && ss_out == nullptr &&
+                             g->rowscale == nullptr && (g->rowss == nullptr || g->ss_slots == 4) && n_half + HALF <= N &&
+                             n_half + HALF <= p_cols && (Cp == nullptr || n_half + HALF <= c_col0) &&
+                             (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+      if (row_owner) {
+        const int row = m_base + lane;
+        const int rowc = min(row, M - 1);
+        float rs = 1.0f;
+        if (g->rowss != nullptr) {   // fused RMSNorm: F.normalize(x, dim=-1) of the GEMM input (bs_roformer.py:49)
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(g->rowss) + rowc);
+          rs = 1.0f / fmaxf(sqrtf(((s4.x + s4.y) + s4.z) + s4.w), 1e-12f);
+        }
+        int64_t rot_row = 0;   // float4 index of this row's (cos, sin) pairs in the rotary table
+        if (FLAVOR == F_ROT && rot_cols > 0) rot_row = (int64_t)((row / ep.pos_div) % ep.pos_mod) * (ep.rot_dim >> 2);
+        {   // bias slice of the warp's columns -> shared memory (lane -> 4 consecutive columns)
+          float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias != nullptr && lane * 4 < HALF) bq = __ldg(reinterpret_cast<const float4*>(bias + n_half) + lane);   // interior tile: in range
+          if (lane * 4 < HALF) sts128(bias_s + lane * 16, bq);
+          __syncwarp();
+        }
+        const void* mapP = &groups[gi].mapP;
+        tc::mbar_wait(&tmem_full[as], aph);
+        tc::tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + ch * HALF;
+        float v[EPI_COLS];
+        tmem_ld16(t_row, v);
+#pragma unroll 1
+        for (int c = 0; c < HALF / EPI_COLS; ++c) {
+          const int n = n_half + c * EPI_COLS;
+          const bool do_rot = FLAVOR == F_ROT && n < rot_cols;
+          float4 cs[4];
+          if (do_rot) {
+            const float4* rp = reinterpret_cast<const float4*>(ep.rot) + rot_row + ((n % ep.rot_dim) >> 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cs[k] = __ldg(rp + k);
+          }
+          float4 o[4];
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 b4 = lds128(bias_s + (c * EPI_COLS + 4 * k) * 4);
+            o[k].x = fmaf(v[4 * k], rs, b4.x);
+            o[k].y = fmaf(v[4 * k + 1], rs, b4.y);
+            o[k].z = fmaf(v[4 * k + 2], rs, b4.z);
+            o[k].w = fmaf(v[4 * k + 3], rs, b4.w);
+          }
+          if (c + 1 < HALF / EPI_COLS) tmem_ld16(t_row + (c + 1) * EPI_COLS, v);
+          if (FLAVOR == F_GELU) gelu_fast16(o);
+          if (FLAVOR == F_TANH) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { o[k].x = tanhf(o[k].x); o[k].y = tanhf(o[k].y); o[k].z = tanhf(o[k].z); o[k].w = tanhf(o[k].w); }
+          }
+          if (do_rot) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float x1 = o[k].x, x2 = o[k].y, x3 = o[k].z, x4 = o[k].w;
+              o[k].x = x1 * cs[k].x - x2 * cs[k].y;
+              o[k].y = x2 * cs[k].x + x1 * cs[k].y;
+              o[k].z = x3 * cs[k].z - x4 * cs[k].w;
+              o[k].w = x4 * cs[k].z + x3 * cs[k].w;
+            }
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc::split_bf16x2(o[k].x, o[k].y, hi[2 * k], lo[2 * k]);
+            tc::split_bf16x2(o[k].z, o[k].w, hi[2 * k + 1], lo[2 * k + 1]);
+          }
+          // the previous step's boxes must have been read by TMA before the staging buffer is rewritten
+          if (c > 0) {
+            if (lane == 0) tc::bulk_wait_read0();
+            __syncwarp();
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 32), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 32 + 16), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+          if (two_planes) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + 1024 + lane * 32), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + 1024 + lane * 32 + 16), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+          }
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tc::tma_store_3d(mapP, stage, n, m_base, 0);
+            if (two_planes) tc::tma_store_3d(mapP, stage + 1024, n, m_base, 1);
+            tc::bulk_commit();
+          }
+        }
+        if (lane == 0) tc::bulk_wait_read0();   // the staging buffer is free for the next tile (either path)
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) tc::mbar_arrive_leader(&tmem_empty[as]); else tc::mbar_arrive(&tmem_empty[as]);
+        }
+      } else {
       // per-lane constants of the 4 rows this lane finishes in phase B (rows it*8 + rb of the warp's 32)
       float rs4[4];
       int64_t orow4[4];
@@ -620,8 +724,10 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
           if (c4 == 0 && ok4[it]) ss_out[orow4[it] * ss_ld + NCH * nb + ch] = v;
         }
       }
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (lane == 0) tc::bulk_wait0();   // every TMA store of this warp has completed before the CTA may exit
   }
 
   tc::tc_fence_before();
@@ -700,8 +806,9 @@ sesa_encode_tiled_fn sesa_get_encode_tiled() {
   return fn;
 }
 
-int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                        const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+static int make_tmap_bf16_impl(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                               const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                               CUtensorMapSwizzle swizzle) {
   sesa_encode_tiled_fn enc = sesa_get_encode_tiled();
   if (enc == nullptr) {
     sesa_set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -717,7 +824,7 @@ int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     sesa_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, stride0 %llu B)", (int)r,
@@ -726,6 +833,15 @@ int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint
     return SESA_ERR_CUDA;
   }
   return SESA_OK;
+}
+
+int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return make_tmap_bf16_impl(map, base, rank, dims, strides_bytes, box, elem_strides, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int sesa_make_tmap_bf16_plain(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                              const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_bf16_impl(map, base, rank, dims, strides_bytes, box, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 extern "C" int64_t sesa_gemm_tc_table_bytes(int n_groups) { return (int64_t)sizeof(TcGroup) * (n_groups > 0 ? n_groups : 0); }
@@ -809,6 +925,15 @@ extern "C" int sesa_gemm_tc_build(const sesa_tc_problem* pr, int n_groups, int b
                    "sesa_gemm_tc_build: problem %d: ss_out needs 16-byte aligned fp32 output rows", i);
     SESA_CHECK_ARG(p.c_col0 >= 0 && (p.c_col0 & 3) == 0 && p.p_cols >= 0 && (p.p_cols & 3) == 0,
                    "sesa_gemm_tc_build: problem %d: p_cols / c_col0 must be multiples of 4", i);
+    g.p_tma = 0;
+    if (p.P != nullptr && p.row_map == 0 && (p.ldp & 7) == 0 && (p.p_plane & 7) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.P) & 15) == 0) {
+      const uint64_t pc = (uint64_t)(p.p_cols > 0 ? p.p_cols : p.N);
+      const uint64_t dimsP[3] = {pc, (uint64_t)p.M, (uint64_t)(p.p_plane > 0 ? 2 : 1)};
+      const uint64_t strP[2] = {(uint64_t)p.ldp * 2, (uint64_t)(p.p_plane > 0 ? p.p_plane : p.ldp * (int64_t)p.M) * 2};
+      const uint32_t boxP[3] = {EPI_COLS, 32, 1};
+      if (pc >= EPI_COLS && sesa_make_tmap_bf16_plain(&g.mapP, p.P, 3, dimsP, strP, boxP) == SESA_OK) g.p_tma = 1;
+    }
     g.C = p.C;
     g.P = reinterpret_cast<__nv_bfloat16*>(p.P);
     g.ldc = p.ldc;

@@ -76,6 +76,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* map, uint64_t
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// shared memory (byte address in the shared window) -> global through a tensor map; completion is tracked by bulk groups
+__device__ __forceinline__ void tma_store_3d(const void* map, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every committed bulk store has finished READING its shared-memory source (which may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// every committed bulk store is complete
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(void* dst, const void* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -286,5 +297,8 @@ typedef CUresult (*sesa_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuui
                                          CUtensorMapFloatOOBfill);
 sesa_encode_tiled_fn sesa_get_encode_tiled();
 // bf16 tensor of `rank` dims (dims[0] innermost, strides_bytes[i] = byte stride of dim i+1), 128B-swizzled boxes.
+// same, without shared-memory swizzling (dense row-major boxes: the epilogue's TMA stores)
+int sesa_make_tmap_bf16_plain(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                              const uint64_t* strides_bytes, const uint32_t* box);
 int sesa_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
