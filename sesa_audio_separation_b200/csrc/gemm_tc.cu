@@ -385,16 +385,22 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + ch * HALF;
         float v[EPI_COLS];
         tmem_ld16(t_row, v);
+        // (cos, sin) pairs of this row for the step's 8 column pairs: requested one step ahead, right after the previous
+        // step's rotation has consumed the registers
+        float4 cs[4];
+        auto load_cs = [&](int cstep) {
+          const int nn = n_half + cstep * EPI_COLS;
+          if (FLAVOR == F_ROT && cstep < HALF / EPI_COLS && nn < rot_cols) {
+            const float4* rp = reinterpret_cast<const float4*>(ep.rot) + rot_row + ((nn % ep.rot_dim) >> 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cs[k] = __ldg(rp + k);
+          }
+        };
+        load_cs(0);
 #pragma unroll 1
         for (int c = 0; c < HALF / EPI_COLS; ++c) {
           const int n = n_half + c * EPI_COLS;
           const bool do_rot = FLAVOR == F_ROT && n < rot_cols;
-          float4 cs[4];
-          if (do_rot) {
-            const float4* rp = reinterpret_cast<const float4*>(ep.rot) + rot_row + ((n % ep.rot_dim) >> 2);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cs[k] = __ldg(rp + k);
-          }
           float4 o[4];
           tc::tmem_ld_wait();
 #pragma unroll
@@ -421,6 +427,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               o[k].w = x4 * cs[k].z + x3 * cs[k].w;
             }
           }
+          load_cs(c + 1);
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
