@@ -77,7 +77,9 @@ int sesa_stft(const float* audio, float* spec, const float* window, const float*
 /* complex mask multiply (bs_roformer.py:556-567; Mel scatter-average mel_band_roformer.py:603-616) fused with
  * torch.istft (bs_roformer.py:575): irFFT, window, overlap-add over frames, / window envelope, trim.
  * mode 0: mask[n][b*T+t][f][c][2]; mode 1: mask[n][b*T+t][J][2] + inv_index[(f*C+c)*2+{0,1}], inv_count[f*C+c];
- * mode 2: no mask, spec[(b*nstems+n)][t][f][c][2].  out[b][n][c][out_len]; envelope[out_len]. */
+ * mode 2: no mask, spec[(b*nstems+n)][t][f][c][2].  out[b][n][c][out_len] (contiguous, fully overwritten; for
+ * n_fft 2048 it is zero-filled on the stream first and accumulated with order-independent two-term atomics, so the
+ * result is bitwise reproducible and independent of the batch); envelope[out_len]. */
 int sesa_mask_istft(const float* spec, const float* mask, const int32_t* inv_index, const float* inv_count,
                     float* out, const float* window, const float* envelope, const float* twiddle, int batch,
                     int nstems, int channels, int n_fft, int hop, int n_frames, int64_t out_len, int mode,

@@ -9,7 +9,9 @@
 //     own 128 rows of A and half of the W tile, the leader issues the MMAs, commits are multicast to both CTAs;
 //   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled 64-wide K slabs, mbarrier ring), warp 1 =
 //     single-thread tcgen05.mma issuer with fp32 accumulators in TMEM (two BN-column buffers: the epilogue of tile i
-//     overlaps the main loop of tile i+1), warps 2-9 = epilogue (tcgen05.ld -> smem transpose -> coalesced phase);
+//     overlaps the main loop of tile i+1), warps 2-9 = epilogue: for planes-only outputs the thread that reads an
+//     accumulator row finishes it and TMA stores the bf16 boxes (row-owner path); outputs that carry the fp32 residual
+//     stream go tcgen05.ld -> smem transpose -> coalesced phase;
 //   * fp32 parity on bf16 tensor cores: operands are bf16 hi/lo planes and each K slab issues
 //     Ahi.Whi + Ahi.Wlo + Alo.Whi into the same fp32 TMEM accumulator (NSPLIT = 3); NSPLIT = 1 is plain bf16;
 //   * the epilogue fuses row scale (RMSNorm, from per-row sum-of-squares slots), bias, GELU/tanh/sigmoid, rotary
