@@ -353,7 +353,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
           if (grow) mref = mnew;
         }
         const float moff = (mref == -INFINITY ? 0.f : mref) * LOG2E;
-        float sum = 0.f;
+        float2 sum2 = make_float2(0.f, 0.f);
         // P leaves for tensor memory in two halves of 16 keys (8 packed registers per plane): keeps the live registers of
         // the loop under the 96 the two-CTA residency allows
 #pragma unroll
@@ -361,16 +361,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
           uint32_t phi[HC / 4], plo[HC / 4];
 #pragma unroll
           for (int e = 0; e < HC / 4; ++e) {
-            const float p0 = tc::ex2_approx(fmaf(s[hh * (HC / 2) + 2 * e], LOG2E, -moff));
-            const float p1 = tc::ex2_approx(fmaf(s[hh * (HC / 2) + 2 * e + 1], LOG2E, -moff));
-            sum += p0 + p1;
-            tc::split_bf16x2(p0, p1, phi[e], plo[e]);
+            // packed fp32x2 arithmetic (FFMA2 / FADD2): exponent argument, row sum and hi/lo residual of a key pair
+            const float2 a = __ffma2_rn(make_float2(s[hh * (HC / 2) + 2 * e], s[hh * (HC / 2) + 2 * e + 1]),
+                                        make_float2(LOG2E, LOG2E), make_float2(-moff, -moff));
+            const float2 pp = make_float2(tc::ex2_approx(a.x), tc::ex2_approx(a.y));
+            sum2 = __fadd2_rn(sum2, pp);
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(phi[e]) : "f"(pp.y), "f"(pp.x));
+            const float2 hf = make_float2(__uint_as_float(phi[e] << 16), __uint_as_float(phi[e] & 0xffff0000u));
+            const float2 r = __ffma2_rn(hf, make_float2(-1.0f, -1.0f), pp);      // p - hi(p), exact
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(plo[e]) : "f"(r.y), "f"(r.x));
           }
           tc::tmem_st8(tmem_SP + st * 64 + lane_off + hf * (HC / 2) + hh * (HC / 4), phi);
           if (NSPLIT == 3) tc::tmem_st8(tmem_SP + st * 64 + lane_off + 32 + hf * (HC / 2) + hh * (HC / 4), plo);
         }
         tc::tmem_st_wait();
-        lrun += sum;
+        lrun += sum2.x + sum2.y;
         tc::tc_fence_before();
         tc::mbar_arrive(&p_full[st]);
       }
