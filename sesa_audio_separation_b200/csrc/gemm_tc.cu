@@ -685,8 +685,12 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
               const int oc = colb >> 1;
               if (Cp != nullptr) {
                 float* cp = Cp + orow * ldc + oc;
-                if (colb + 1 < N) cp[0] = g0;
-                if (colb + 3 < N) cp[1] = g1;
+                if (colb + 3 < N && ((reinterpret_cast<uintptr_t>(cp) & 7) == 0)) {
+                  *reinterpret_cast<float2*>(cp) = make_float2(g0, g1);   // 4 lanes x 8 bytes: one full sector per row
+                } else {
+                  if (colb + 1 < N) cp[0] = g0;
+                  if (colb + 3 < N) cp[1] = g1;
+                }
               }
               if (Pp != nullptr) {
                 __nv_bfloat16 h, l;
