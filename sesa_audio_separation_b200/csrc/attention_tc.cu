@@ -219,25 +219,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map, AttnParams p) {
       // boundaries (nblk may be 1).
       const int n_items = blockIdx.x < total ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
       const uint32_t GB = (uint32_t)n_items * (uint32_t)nblk;
+      // Q lives in tensor memory for the whole item (columns [192, 256): hi plane 32 columns, lo plane 32): it is copied
+      // there once per item (tcgen05.cp, in issue order with the MMAs), so the score MMAs read their A operand from TMEM
+      // like P V does and only K crosses the shared-memory port (an SS-form 128x64x16 MMA fetches 6 KB per 32 cycles:
+      // more than the 128 B/clk the port delivers)
+      const uint32_t tmem_Q = tmem_base + 192;
       auto issue_s = [&](uint32_t g) {
         const int n = (int)(g / (uint32_t)nblk);
         const int j = (int)(g - (uint32_t)n * (uint32_t)nblk);
         const int st = g & 1;
-        if (j == 0) tc::mbar_wait(q_full, n & 1);
+        if (j == 0) {
+          tc::mbar_wait(q_full, n & 1);
+          tc::tc_fence_after();
+#pragma unroll
+          for (int pl = 0; pl < C::NP; ++pl)
+#pragma unroll
+            for (int ks = 0; ks < DH / 16; ++ks)
+              tc::tmem_cp_128x256b(tmem_Q + pl * 32 + ks * 8, tc::make_smem_desc_sw128(aQ + pl * C::Q_BYTES + ks * 32));
+          tc::umma_commit(q_empty);   // the Q tile in shared memory may be overwritten once the copies retire
+        }
         tc::mbar_wait(&k_full[st], (g >> 1) & 1);
         tc::tc_fence_after();
 #pragma unroll
         for (int prod = 0; prod < NSPLIT; ++prod) {
-          const uint32_t qa = aQ + (prod == 2 ? C::Q_BYTES : 0);
+          const uint32_t qa = tmem_Q + (prod == 2 ? 32 : 0);
           const uint32_t ka = aK + (st * C::NP + (prod == 1 ? 1 : 0)) * C::KV_BYTES;
 #pragma unroll
           for (int ks = 0; ks < DH / 16; ++ks)
-            tc::umma_f16(tmem_SP + st * 64, tc::make_smem_desc_sw128(qa + ks * 32), tc::make_smem_desc_sw128(ka + ks * 32),
-                         idesc_s, (prod | ks) != 0 ? 1u : 0u);
+            tc::umma_f16_ts(tmem_SP + st * 64, qa + ks * 8, tc::make_smem_desc_sw128(ka + ks * 32), idesc_s,
+                            (prod | ks) != 0 ? 1u : 0u);
         }
         tc::umma_commit(&s_full[st]);
         tc::umma_commit(&k_empty[st]);
-        if (j == nblk - 1) tc::umma_commit(q_empty);   // Q may be overwritten once these MMAs retire
       };
       if (GB > 0) issue_s(0);
       if (GB > 1) issue_s(1);

@@ -185,6 +185,11 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// shared memory -> tensor memory, 128 rows x 256 bits (= one UMMA_K slice of 16 bf16 per row, 8 TMEM columns): stages an A
+// operand for TS-form MMAs; executes in issue order with the MMAs of the same thread
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t s_desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(s_desc) : "memory");
+}
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // Shared-window addresses of the two CTAs of a pair differ in bit 24; clearing it addresses the even (leader) CTA.
