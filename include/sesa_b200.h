@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SESA_B200_ABI_VERSION 2
+#define SESA_B200_ABI_VERSION 3
 #define SESA_TC_SS_SLOTS_PER_BLOCK 2 /* row-sum-of-squares slots a GEMM writes per column block (one per epilogue warp of a TMEM quadrant) */
 
 enum { SESA_ACT_NONE = 0, SESA_ACT_GELU = 1, SESA_ACT_TANH = 2, SESA_ACT_SIGMOID = 3 };
@@ -224,6 +224,41 @@ int sesa_overlap_add_range(const float* chunk_out, const int64_t* starts, const 
                            const float* window, int nstems, int channels, int64_t p_begin, int64_t p_end,
                            const float* init, int64_t init_p0, int64_t init_len, int mode, int64_t crop,
                            int64_t out_len, float* out, void* stream);
+
+/* ---- streaming overlap-add (the product path of utils.py:439-464) ---------------------------- */
+/* Folds the model outputs y[nb][n][c][L] of chunks [k0, k0+nb) into the track result, one call per engine batch, in
+ * ascending chunk order per sample (result += x * window).  The padded mix is cut into step-long regions; regions
+ * [r_begin, r_end) are processed.  A region whose earlier chunks were folded before (by an earlier call, or by the
+ * previous rank of a chunk-range shard whose raw sums were copied in as the halo) continues from
+ * partial[n*c][part_ld] (padded positions part_p0..); a region with chunks still to come stores its raw sums there;
+ * a region whose last chunk is in this batch is finished: / sum_k w of the GLOBAL schedule, NaN -> 0
+ * (utils.py:457-459), cropped by `crop` (:462-464) and written to out[n*c][out_ld] at column (p - crop) - out_q0 when
+ * that lies in [0, out_cols) and p - crop in [0, out_len).  partial is never read before it was written, so it needs
+ * no initialisation. */
+int sesa_overlap_accumulate(const float* y, int k0, int nb, const int64_t* starts, const int64_t* lens,
+                            const int32_t* kinds, int n_chunks, int64_t step, int64_t chunk_size, int fade,
+                            const float* window, int nstems, int channels, int64_t padded_len, int r_begin, int r_end,
+                            float* partial, int64_t part_ld, int64_t part_p0, int64_t crop, int64_t out_len, float* out,
+                            int64_t out_ld, int64_t out_q0, int64_t out_cols, void* stream);
+/* dst[c][i] = mix[c][reflect(p0 + i - left)], i in [0, count): the border reflect pad of utils.py:391-393 for one
+ * slice [p0, p0+count) of the padded mix, reading a window src[c][src_cols] that holds mix[:, src_off : src_off+src_cols)
+ * (a chunk-range shard uploads only the samples its chunks touch). */
+int sesa_pad_reflect_slice(const float* src, int64_t src_cols, int64_t src_off, float* dst, int channels, int64_t len,
+                           int64_t left, int64_t p0, int64_t count, void* stream);
+
+/* ---- test-time augmentation (utils.py:241-292) ----------------------------------------------- */
+/* swapped[c] = mix[C-1-c] (mix[::-1].copy(), :271), negated = -1.0 * mix (:271). */
+int sesa_tta_variants(const float* mix, float* swapped, float* negated, int channels, int64_t len, void* stream);
+/* out[n][c] = ((orig[n][c] + swapped_est[n][C-1-c]) - negated_est[n][c]) / 3 — the += / -= / /= sequence of :283-290. */
+int sesa_tta_combine(const float* orig, const float* swapped_est, const float* negated_est, float* out, int nstems,
+                     int channels, int64_t len, void* stream);
+
+/* ---- waveform ensembling (ensemble.py:172-183 process_waveform) -------------------------------- */
+/* out[i] = reduce over the n_inputs device arrays inputs_host[m][i] (a HOST array of device pointers), accumulated in
+ * float64 in input order like numpy on the reference's float64 buffers.  method 0: mean, or sum(x*w)/sum(w) when
+ * weights_host (host, float64, already normalised like ensemble.py:293-295) is given; 1: median; 2: max; 3: min. */
+int sesa_ensemble_wave(const float* const* inputs_host, int n_inputs, const double* weights_host, int method, float* out,
+                       int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,12 @@ CASES = {
         dim=64, depth=1, stereo=True, num_stems=2, time_transformer_depth=1, freq_transformer_depth=1,
         num_bands=60, dim_head=64, heads=2, stft_n_fft=2048, stft_hop_length=441, stft_win_length=2048,
         mask_estimator_depth=2, mlp_expansion_factor=2, sample_rate=44100)),
+    # Mel-Band-RoFormer with match_input_audio_length=True on a length the hop does not divide
+    # (istft length = input length, mel_band_roformer.py:505,622-623), mono, 1 stem, 24 mel bands, hop 512
+    'mel_match': dict(kind='mel_band_roformer', seed=15, batch=1, length=512 * 20 + 333, cfg=dict(
+        dim=32, depth=1, stereo=False, num_stems=1, time_transformer_depth=1, freq_transformer_depth=1,
+        num_bands=24, dim_head=64, heads=1, stft_n_fft=2048, stft_hop_length=512, stft_win_length=2048,
+        mask_estimator_depth=1, mlp_expansion_factor=2, sample_rate=44100, match_input_audio_length=True)),
     # MDX23C TFC-TDF-v3, 2 instruments
     'mdx_small': dict(kind='mdx23c', seed=14, batch=2, length=256 * 31, cfg=dict(
         audio=dict(chunk_size=256 * 31, n_fft=1024, hop_length=256, dim_f=512, num_channels=2,
@@ -43,6 +49,23 @@ DEMIX_MODEL_CASES = {
                             batch_size=2, instruments=['vocals', 'other'], target='vocals', seed=22),
     'demix_mel_ov2_b2': dict(model='mel_small', length=441 * 32 * 2 + 333, chunk_size=441 * 32, num_overlap=2,
                              batch_size=2, instruments=['vocals', 'other'], target=None, seed=23),
+}
+
+
+# Per-file flows of inference_pytorch.run_folder_pytorch_optimized (:219-260) run by the UNMODIFIED reference:
+# normalize -> demix -> TTA -> DemudPhaseRemix -> instrumental -> denormalize.  'flow_bs_*' takes the branch without an
+# 'instrumental' stem (:236-242), 'flow_mel_*' the branch with one (:243-250, where apply_tta updates the first pass's
+# estimates in place).
+FLOW_CASES = {
+    'flow_bs_norm_tta_demud': dict(model='bs_small', length=441 * 40 * 2 + 900, chunk_size=441 * 40, num_overlap=2,
+                                   batch_size=2, instruments=['vocals', 'other'], target='vocals', seed=81,
+                                   normalize=True, use_tta=True, demud=True, extract_instrumental=True),
+    'flow_mel_tta_demud_inst': dict(model='mel_small', length=441 * 32 * 2 + 100, chunk_size=441 * 32, num_overlap=2,
+                                    batch_size=1, instruments=['vocals', 'instrumental'], target=None, seed=82,
+                                    normalize=False, use_tta=True, demud=True, extract_instrumental=False),
+    'flow_bs_norm_only': dict(model='bs_small', length=441 * 40 + 4321, chunk_size=441 * 40, num_overlap=4,
+                              batch_size=1, instruments=['vocals', 'other'], target='vocals', seed=83,
+                              normalize=True, use_tta=False, demud=False, extract_instrumental=False),
 }
 
 

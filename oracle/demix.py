@@ -51,8 +51,10 @@ def prefer_target_instrument(training):
     return [ti] if ti else list(training['instruments'])
 
 
-def demix(mix, model_fn, chunk_size, num_overlap, batch_size, num_instruments, return_counter=False):
-    """utils.py:369-464 (generic mode) restated: returns (num_instruments, C, len) float32 ndarray."""
+def demix(mix, model_fn, chunk_size, num_overlap, batch_size, num_instruments, return_counter=False, max_chunks=None):
+    """utils.py:369-464 (generic mode) restated: returns (num_instruments, C, len) float32 ndarray.
+    ``max_chunks`` stops the loop after that many chunks: a BOUNDED TIMING SAMPLE of the same loop for bench.py's CPU
+    baseline (the returned array is then incomplete and must not be used as a result)."""
     mix = torch.as_tensor(np.asarray(mix), dtype=torch.float32)
     sch = demix_schedule(mix.shape[-1], chunk_size, num_overlap, batch_size)
     fade, border = sch['fade'], sch['border']
@@ -82,6 +84,8 @@ def demix(mix, model_fn, chunk_size, num_overlap, batch_size, num_instruments, r
             result[..., s:s + l] += x[j, ..., :l].cpu() * w[:l]
             counter[..., s:s + l] += w[:l]
         k += len(grp)
+        if max_chunks is not None and k >= max_chunks:
+            break
     est = (result / counter).numpy()
     np.nan_to_num(est, copy=False, nan=0.0)
     cnt = counter.numpy()

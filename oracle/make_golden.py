@@ -21,7 +21,7 @@ sys.path.insert(2, '/root/reference')
 warnings.filterwarnings('ignore')
 
 from oracle.weights import fill_state_dict, synth_mix  # noqa: E402
-from oracle.cases import CASES, DEMIX_IDENTITY_CASES, DEMIX_MODEL_CASES, make_input  # noqa: E402
+from oracle.cases import CASES, DEMIX_IDENTITY_CASES, DEMIX_MODEL_CASES, FLOW_CASES, make_input  # noqa: E402
 
 OUT = os.path.join(ROOT, 'tests', 'golden')
 
@@ -51,6 +51,50 @@ def load_seeded(model, seed):
     model.eval()
     csum = float(sum(v.double().sum().item() for v in new.values()))
     return shapes, csum
+
+
+def run_flows():
+    """The per-file flow (normalize / TTA / DemudPhaseRemix / instrumental / denormalize) through the unmodified
+    ``inference_pytorch.run_folder_pytorch_optimized`` (:189-274).  Only file I/O is replaced: ``librosa.load`` hands
+    back the seeded mix and ``soundfile.write`` captures the arrays that would have been written."""
+    import argparse
+    import tempfile
+    import librosa
+    import soundfile
+    from ml_collections import ConfigDict
+
+    box = {}
+    librosa.load = lambda path, sr=None, mono=False: (box['mix'].copy(), sr)
+    soundfile.write = lambda path, data, sr, subtype=None: box['out'].__setitem__(os.path.basename(path), np.array(data).T)
+    import inference_pytorch as ref_inf
+    from pytorch_backend import PyTorchBackend
+
+    # what create_inference_session (pytorch_backend.py:492-536) does on a CPU device; the backend object is made once
+    # because its constructor sets the interop thread count, which torch allows once per process
+    backend = PyTorchBackend(device='cpu', optimize_mode='default')
+    for name, fc in FLOW_CASES.items():
+        case = CASES[fc['model']]
+        model = build_reference_model(case['kind'], case['cfg'])
+        load_seeded(model, case['seed'])
+        cfg = ConfigDict(dict(audio=dict(chunk_size=fc['chunk_size'], sample_rate=44100),
+                              inference=dict(num_overlap=fc['num_overlap'], batch_size=fc['batch_size'],
+                                             **({'normalize': True} if fc['normalize'] else {})),
+                              training=dict(instruments=fc['instruments'], target_instrument=fc['target'],
+                                            use_amp=False)))
+        box['mix'] = synth_mix(fc['length'], 2, seed=fc['seed'])
+        box['out'] = {}
+        with tempfile.TemporaryDirectory() as tmp:
+            os.makedirs(os.path.join(tmp, 'in'))
+            open(os.path.join(tmp, 'in', 'song.wav'), 'wb').close()
+            args = argparse.Namespace(input_folder=os.path.join(tmp, 'in'), store_dir=os.path.join(tmp, 'out'),
+                                      disable_detailed_pbar=True, use_tta=fc['use_tta'],
+                                      demud_phaseremix_inst=fc['demud'], extract_instrumental=fc['extract_instrumental'],
+                                      model_type=case['kind'], export_format='wav FLOAT', flac_file=False,
+                                      pcm_type='PCM_24')
+            backend.optimize_model(model, use_amp=False)
+            ref_inf.run_folder_pytorch_optimized(backend, args, cfg, 'cpu', model=model)
+        np.savez_compressed(os.path.join(OUT, f'{name}.npz'), **box['out'])
+        print(name, {k: v.shape for k, v in box['out'].items()})
 
 
 def main():
@@ -104,6 +148,8 @@ def main():
         res = ref_utils.demix(cfg, model, mix, 'cpu', model_type=case['kind'])
         np.savez_compressed(os.path.join(OUT, f'{name}.npz'), **{k: v for k, v in res.items()})
         print(name, {k: v.shape for k, v in res.items()})
+
+    run_flows()
 
     with open(os.path.join(OUT, 'manifest.json'), 'w') as f:
         json.dump(manifest, f, indent=0, sort_keys=True)

@@ -22,8 +22,11 @@ def rmsnorm(x, gamma):
 
 
 def attention(x, sd, p, heads, dim_head):
-    """models/bs_roformer/bs_roformer.py:106-121 with Attend's explicit softmax path
-    (models/bs_roformer/attend.py:113-126; SDPA on CPU computes the same function)."""
+    """models/bs_roformer/bs_roformer.py:106-121.  The softmax core follows Attend's dispatch
+    (models/bs_roformer/attend.py:76-126): with ``flash_attn=True`` (every shipped config) a CPU tensor goes to
+    ``F.scaled_dot_product_attention`` with all back ends allowed (``cpu_config``, :56,89-93) — this is the reference's
+    stock CPU path and the one the timed CPU baseline must run; a CUDA fp32 tensor takes the explicit einsum softmax
+    (:113-126), which is what the reference needs for fp32 on a GPU (flash-only SDPA rejects fp32, SURVEY a-10)."""
     b, n, _ = x.shape
     xn = rmsnorm(x, sd[p + 'norm.gamma'])
     qkv = F.linear(xn, sd[p + 'to_qkv.weight'])
@@ -32,9 +35,12 @@ def attention(x, sd, p, heads, dim_head):
     freqs = sd[p + 'rotary_embed.freqs']
     q = apply_rotary(q, freqs)
     k = apply_rotary(k, freqs)
-    sim = torch.einsum('bhid,bhjd->bhij', q, k) * (dim_head ** -0.5)
-    attn = sim.softmax(dim=-1)
-    out = torch.einsum('bhij,bhjd->bhid', attn, v)
+    if x.device.type == 'cpu':
+        out = F.scaled_dot_product_attention(q, k, v, dropout_p=0.)
+    else:
+        sim = torch.einsum('bhid,bhjd->bhij', q, k) * (dim_head ** -0.5)
+        attn = sim.softmax(dim=-1)
+        out = torch.einsum('bhij,bhjd->bhid', attn, v)
     gates = F.linear(xn, sd[p + 'to_gates.weight'], sd[p + 'to_gates.bias'])  # b n h
     out = out * gates.permute(0, 2, 1).unsqueeze(-1).sigmoid()
     out = out.permute(0, 2, 1, 3).reshape(b, n, heads * dim_head)
@@ -203,7 +209,14 @@ def mel_band_roformer_forward(sd, cfg, raw_audio):
     masks = torch.view_as_complex(masks)
     spec = torch.view_as_complex(stft_repr.contiguous())[:, None]           # b 1 (f s) t
     idx = freq_indices[None, None, :, None].expand(b, num_stems, -1, t)
-    summed = torch.zeros(b, num_stems, fs, t, dtype=spec.dtype, device=spec.device).scatter_add_(2, idx, masks)
+    if spec.device.type == 'cpu':
+        summed = torch.zeros(b, num_stems, fs, t, dtype=spec.dtype, device=spec.device).scatter_add_(2, idx, masks)
+    else:
+        # torch's COMPLEX scatter_add_ on CUDA was measured to differ from its own CPU result by 6e-3 at full size
+        # (torch 2.11, B200; tools/debug_mel.py).  The same sum on the real view is exact on any device: every bin
+        # receives at most two addends (num_bands_per_freq <= 2) and a + b == b + a.
+        summed = torch.view_as_complex(torch.zeros(b, num_stems, fs, t, 2, dtype=raw_audio.dtype, device=spec.device)
+                                       .index_add_(2, freq_indices, torch.view_as_real(masks)))
     denom = nbpf.to(raw_audio.device).repeat_interleave(s)[:, None]          # '(f r) 1'
     spec = spec * (summed / denom.clamp(min=1e-8))
     y = _istft(spec, s, n_fft, hop, win, window, length)

@@ -86,6 +86,14 @@ _SIGS = {
     'sesa_overlap_add_range': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64,
                                        c_int, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                        c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    'sesa_overlap_accumulate': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int,
+                                        c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_int64, c_int64, c_int64,
+                                        c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    'sesa_pad_reflect_slice': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
+                                       c_void_p]),
+    'sesa_tta_variants': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    'sesa_tta_combine': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
+    'sesa_ensemble_wave': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -105,7 +113,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.sesa_abi_version() != 2:
+    if lib.sesa_abi_version() != 3:
         raise SesaError('libsesa_b200.so ABI version mismatch')
     _lib = lib
     return lib
@@ -122,7 +130,8 @@ LAUNCHES = 0
 _profile = None   # dict: class -> [ (start_event, end_event), ... ] when enabled
 _CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_band_prep': 'prep_rows', 'sesa_instnorm_stats': 'norm', 'sesa_norm_act_split': 'norm', 'sesa_transpose_add': 'norm', 'sesa_attention_simt': 'attention',
           'sesa_attention_tc': 'attention', 'sesa_stft': 'stft', 'sesa_mask_istft': 'mask_istft',
-          'sesa_overlap_add': 'overlap_add', 'sesa_overlap_add_range': 'overlap_add', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}
+          'sesa_overlap_add': 'overlap_add', 'sesa_overlap_add_range': 'overlap_add', 'sesa_overlap_accumulate': 'overlap_add', 'sesa_pad_reflect_slice': 'framing',
+          'sesa_tta_variants': 'tta', 'sesa_tta_combine': 'tta', 'sesa_ensemble_wave': 'ensemble', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}
 
 
 def profile_start():

@@ -2,17 +2,28 @@
 
 Rank r runs the model on the contiguous chunk range ``shard_chunks(n_chunks, world, r)`` and owns the padded
 positions from its first chunk's start up to the next rank's first chunk's start.  Chunk k covers
-``[k*step, k*step + L)``, so the owned positions of rank r+1 also receive contributions from the last
-``num_overlap - 1`` chunks of rank r: rank r sends those raw partial sums (``border = L - step`` samples per
-stem/channel) to rank r+1 with ONE send/recv pair per boundary — the only data-path exchange.  The window kind of
-every chunk and the ``counter`` divisor are functions of the global schedule and are recomputed locally (never
-exchanged).  Because the receiver SEEDS its accumulator with the sender's sums and then adds its own chunks in
-ascending order, the floating-point addition order equals the reference's single loop (utils.py:439-442) and the
+``[k*step, k*step + L)``, so the first ``span - 1`` step-long regions owned by rank r+1 (``span = ceil(L / step)``) also
+receive contributions from the last ``span - 1`` chunks of rank r: rank r sends those raw partial sums
+(``~(L - step)`` samples per stem/channel) to rank r+1 with ONE send/recv pair per boundary — the only data-path
+exchange.  The window kind of every chunk and the window-sum divisor are functions of the global schedule and are
+recomputed locally (never exchanged).  Because the receiver CONTINUES from the sender's sums and then adds its own chunks
+in ascending order, the floating-point addition order equals the reference's single loop (utils.py:439-442) and the
 sharded result is bit-identical to the unsharded one.
 
-``ops`` abstracts the two device operations so that the choreography is testable on CPU with gloo
-(tests/test_distributed.py provides a torch-CPU ``ops``; the product path passes CUDA closures over
-``sesa_overlap_add_range``).
+Schedule of one rank (``run_sharded_track``), built so that no rank ever waits for a neighbour's model passes:
+
+1. post the receive of the incoming halo;
+2. TAIL FIRST: run the model on the rank's LAST chunks (at least ``span - 1`` of them), fold them into the regions the
+   next rank owns (those depend on nothing else), and post the halo send at once — it crosses NVLink while every rank is
+   still busy with the rest of its range; the tail outputs are kept;
+3. walk the remaining chunks in ascending engine batches, each folded into the running sums as soon as its forward is
+   done (``sesa_overlap_accumulate``); the first fold continues from the received halo;
+4. fold the kept tail outputs into the rank's own regions (ascending order is preserved: they are its last chunks);
+5. gather the disjoint finished ranges on the root: one grouped set of point-to-point receives straight into the rows
+   of the result (no staging buffer, no reduction collective).
+
+``ops`` abstracts the device work so that the choreography is testable on CPU with gloo (tests/test_distributed.py
+provides a torch-CPU ``ops``; the product path passes CUDA closures over the C-ABI, demix.py).
 """
 import torch
 import torch.distributed as dist
@@ -44,59 +55,117 @@ def shard_layout(plan, world):
     return out
 
 
-def sharded_overlap_add(plan, world, rank, n_rows, ops, device, group=None, gather_root=0):
-    """Run the halo exchange and the owned-range finish; returns the full cropped result [n_rows, out_len] on
-    ``gather_root`` (None elsewhere).  ops.raw(p0, p1) -> tensor [n_rows, p1-p0] of this rank's raw sums;
-    ops.final(p0, p1, init, init_p0) -> tensor [n_rows, q1-q0] of finished samples for the cropped range
-    [q0, q1) = [max(p0,crop), min(p1, crop+out_len)) - crop."""
+def cropped_range(plan, begin, end):
+    """Owned padded range [begin, end) -> the range [q0, q1) of result samples it finishes (after the border crop)."""
+    crop = plan.border if plan.pad else 0
+    q0 = min(max(begin - crop, 0), plan.length)
+    q1 = min(max(end - crop, q0), plan.length)
+    return q0, q1
+
+
+def _peer(group, r):
+    """Rank r OF THE GROUP as the global rank torch.distributed's point-to-point calls expect."""
+    return dist.get_global_rank(group, r) if group is not None else r
+
+
+def tail_size(n_own, span, engine_batch):
+    """Chunks a non-last rank runs first: at least span-1 (everything the next rank's regions depend on), and sized so
+    that the remaining chunks split into full engine batches."""
+    rem = n_own % engine_batch or engine_batch
+    return min(n_own, max(span - 1, rem))
+
+
+def run_sharded_track(plan, world, rank, ops, engine_batch, group=None, stats=None):
+    """One rank's share of a chunk-range-sharded track.  ``ops`` provides
+      forward(k0, nb, keep) -> y            model outputs of chunks [k0, k0+nb) ([nb, rows, L]); keep=True: own storage
+      accumulate(y, k0, nb, r0, r1)         fold into regions [r0, r1) (sesa_overlap_accumulate)
+      read_partial(p0, p1) -> tensor        contiguous copy [rows, p1-p0] of the running sums
+      seed_partial(p0, tensor)              store received sums at padded position p0
+      empty(rows, cols) -> tensor           scratch on the ops' device
+      mark(name)                            optional timing hook
+    and leaves the finished owned range in ops' output buffer.  Returns (outstanding send request, its buffer) or
+    (None, None); the caller waits on the request before releasing the buffer."""
     layout = shard_layout(plan, world)
     lo, hi, begin, end = layout[rank]
+    if hi <= lo:
+        return None, None
     active = [r for r in range(world) if layout[r][1] > layout[r][0]]
-    crop = plan.border if plan.pad else 0
-    out_len = plan.length
-    L = plan.chunk_size
-    reqs = []
-    mine = None
-    if hi > lo:
-        idx = active.index(rank)
-        halo = None
-        halo_p0 = 0
-        if idx > 0:                                   # receive the previous rank's tail sums
-            prev = active[idx - 1]
-            plo, phi = layout[prev][0], layout[prev][1]
-            halo_p0 = begin
-            halo_len = min(plan.padded, plan.starts[phi - 1] + L) - begin
-            halo = torch.empty(n_rows, max(halo_len, 0), device=device, dtype=torch.float32)
-            if halo_len > 0:
-                reqs.append(dist.irecv(halo, src=prev, group=group))
-        if idx + 1 < len(active):                     # send our tail sums to the next rank
-            nxt = active[idx + 1]
-            p0 = end
-            p1 = min(plan.padded, plan.starts[hi - 1] + L)
-            if p1 > p0:
-                tail = ops.raw(p0, p1).contiguous()
-                reqs.append(dist.isend(tail, dst=nxt, group=group))
-        for q in reqs:
-            q.wait()
-        mine = ops.final(begin, end, halo if (halo is not None and halo.shape[1] > 0) else None, halo_p0)
-    # gather the disjoint owned ranges on the root (send/recv; no reduction collective on the data path)
-    def cropped(b, e):
-        return max(b, crop) - crop, max(min(e, crop + out_len) - crop, max(b, crop) - crop)
+    idx = active.index(rank)
+    prev = active[idx - 1] if idx > 0 else None
+    nxt = active[idx + 1] if idx + 1 < len(active) else None
+    step, L = plan.step, plan.chunk_size
+    span = -(-L // step)
+    n_regions = -(-plan.padded // step)
+    mark = getattr(ops, 'mark', lambda name: None)
+
+    halo, req_in = None, None
+    if prev is not None:
+        halo_p1 = min(plan.padded, (lo + span - 1) * step)
+        if halo_p1 > begin:
+            halo = ops.empty(ops.rows, halo_p1 - begin)
+            req_in = dist.irecv(halo, src=_peer(group, prev), group=group)
+
+    def seed():
+        nonlocal req_in
+        if req_in is not None:
+            mark('halo_wait_begin')
+            req_in.wait()
+            ops.seed_partial(begin, halo)
+            mark('halo_wait_end')
+            req_in = None
+
+    n_tail, y_tail, req_out, sent = 0, None, None, None
+    if nxt is not None:
+        n_tail = tail_size(hi - lo, span, engine_batch)
+        y_tail = ops.forward(hi - n_tail, n_tail, True)
+        r1 = min(hi + span - 1, n_regions)
+        ops.accumulate(y_tail, hi - n_tail, n_tail, hi, r1)
+        p1 = min(plan.padded, r1 * step)
+        if p1 > end:
+            sent = ops.read_partial(end, p1)
+            req_out = dist.isend(sent, dst=_peer(group, nxt), group=group)
+            if stats is not None:
+                stats['halo_bytes'] = sent.numel() * sent.element_size()
+    k = lo
+    while k < hi - n_tail:
+        nb = min(engine_batch, hi - n_tail - k)
+        y = ops.forward(k, nb, False)
+        seed()
+        ops.accumulate(y, k, nb, k, min(k + nb + span - 1, n_regions if nxt is None else hi))
+        k += nb
+    if n_tail:
+        seed()
+        ops.accumulate(y_tail, hi - n_tail, n_tail, hi - n_tail, hi)
+    return req_out, sent
+
+
+def gather_owned(plan, world, rank, out, out_q0, make_result, group=None, gather_root=0):
+    """Collect every rank's finished range on ``gather_root``.  ``out`` is this rank's [rows, >= q1-q0] buffer whose
+    column 0 is result sample ``out_q0``; ``make_result()`` allocates the full [rows, length] result on the root (it may
+    alias ``out``).  Receives go row by row straight into the result (each row slice is contiguous) as one grouped set of
+    point-to-point operations; there is no reduction collective on the data path."""
+    layout = shard_layout(plan, world)
+    active = [r for r in range(world) if layout[r][1] > layout[r][0]]
+    ops = []
+    result = None
     if rank == gather_root:
-        result = torch.zeros(n_rows, out_len, device=device, dtype=torch.float32)
+        result = make_result()
         for r in active:
-            q0, q1 = cropped(layout[r][2], layout[r][3])
+            q0, q1 = cropped_range(plan, layout[r][2], layout[r][3])
             if q1 <= q0:
                 continue
             if r == rank:
-                result[:, q0:q1] = mine
-            else:
-                buf = torch.empty(n_rows, q1 - q0, device=device, dtype=torch.float32)
-                dist.recv(buf, src=r, group=group)
-                result[:, q0:q1] = buf
-        return result
-    if hi > lo:
-        q0, q1 = cropped(begin, end)
+                if out is not None and not (out.data_ptr() == result.data_ptr() and out_q0 == 0):
+                    result[:, q0:q1] = out[:, q0 - out_q0:q1 - out_q0]
+                continue
+            for row in range(result.shape[0]):
+                ops.append(dist.P2POp(dist.irecv, result[row, q0:q1], _peer(group, r), group))
+    elif layout[rank][1] > layout[rank][0]:
+        q0, q1 = cropped_range(plan, layout[rank][2], layout[rank][3])
         if q1 > q0:
-            dist.send(mine.contiguous(), dst=gather_root, group=group)
-    return None
+            for row in range(out.shape[0]):
+                ops.append(dist.P2POp(dist.isend, out[row, q0 - out_q0:q1 - out_q0], _peer(group, gather_root), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return result

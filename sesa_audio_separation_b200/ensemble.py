@@ -1,8 +1,9 @@
 """Waveform-domain ensembling (reference: ensemble.py:172-183 process_waveform, CLI :409-438) — SURVEY §8f rank 1.
 
 ``ensemble_waveforms`` is the in-memory form (the reference round-trips every stem through disk and averages 32768-frame
-buffers in numpy): stems that are still on the GPU are combined there with torch tensor ops on the device (a pure
-HBM-bound elementwise pass), numpy inputs are combined on the host exactly like the reference.  The CLI keeps the
+buffers in numpy): stems that are still on the GPU are combined there by one launch of ``sesa_ensemble_wave`` (a pure
+HBM-bound elementwise pass, float64 accumulation in input order), numpy inputs are combined on the host exactly like
+the reference.  The CLI keeps the
 reference's argv (``--files --type --weights --output --buffer``) and PCM_24 output, exit status 0/1.
 The spectral modes (``*_fft``) are out of scope.
 """
@@ -26,23 +27,50 @@ def ensemble_waveforms(stems, method='avg_wave', weights=None):
     if weights is not None and len(weights) != len(stems):
         raise ValueError('one weight per input is required')
     if isinstance(stems[0], torch.Tensor):
-        x = torch.stack([s.to(torch.float32) for s in stems], 0)
-        if method == 'avg_wave':
-            if weights is None:
-                return x.mean(0)
-            w = torch.tensor(weights, dtype=torch.float32, device=x.device)
-            return (x * w.view(-1, 1, 1)).sum(0) / w.sum()
-        if method == 'median_wave':      # np.median averages the two middle values for an even count
-            s, _ = x.sort(0)
-            n = x.shape[0]
-            return s[n // 2] if n % 2 else 0.5 * (s[n // 2 - 1] + s[n // 2])
-        return x.max(0).values if method == 'max_wave' else x.min(0).values
-    chunks = np.stack([np.asarray(s) for s in stems], 0)
+        return _ensemble_device(stems, method, weights)
+    chunks = np.stack([np.asarray(s, dtype=np.float64) for s in stems], 0)     # sf.SoundFile.read -> float64 (:330)
     if method == 'avg_wave':
-        return np.average(chunks, axis=0, weights=weights) if weights is not None else np.mean(chunks, axis=0)
+        if weights is not None:
+            return np.average(chunks, axis=0, weights=_normalised_weights(weights))
+        return np.mean(chunks, axis=0)
     if method == 'median_wave':
         return np.median(chunks, axis=0)
     return np.max(chunks, axis=0) if method == 'max_wave' else np.min(chunks, axis=0)
+
+
+def _normalised_weights(weights):
+    """ensemble.py:292-295: float32 weights divided by their float32 sum."""
+    w = np.array(weights, dtype=np.float32)
+    w /= w.sum()
+    return w
+
+
+def _ensemble_device(stems, method, weights):
+    """Stems still resident on the GPU (e.g. DemixEngine.run(to_host=False) of several models): one pass of
+    sesa_ensemble_wave, accumulating in float64 in input order like numpy does on the reference's float64 buffers."""
+    import ctypes
+    from ._lib import call, require_cuda
+    require_cuda()
+    dev = stems[0].device
+    if dev.type != 'cuda':
+        raise RuntimeError('torch inputs must be CUDA tensors (host arrays are combined with numpy like the reference)')
+    xs = [s.to(device=dev, dtype=torch.float32).contiguous() for s in stems]
+    if any(x.shape != xs[0].shape for x in xs):
+        raise ValueError('all inputs must have the same shape')
+    out = torch.empty_like(xs[0])
+    ptrs = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+    wts = None
+    if weights is not None:
+        if method != 'avg_wave':
+            weights = None
+        else:
+            w = _normalised_weights(weights).astype(np.float64)
+            wts = (ctypes.c_double * len(xs))(*w.tolist())
+    with torch.cuda.device(dev):
+        call('sesa_ensemble_wave', ctypes.cast(ptrs, ctypes.c_void_p), len(xs),
+             ctypes.cast(wts, ctypes.c_void_p) if wts is not None else None, WAVE_METHODS.index(method), out.data_ptr(),
+             out.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return out
 
 
 def run_ensemble(files, method, output_path, weights=None, buffer_size=32768):

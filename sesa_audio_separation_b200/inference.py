@@ -17,7 +17,7 @@ from . import _lib
 from .audio_io import load_audio, write_audio
 from .backend import create_inference_session
 from .config import get_model_from_config, prefer_target_instrument
-from .demix import apply_tta, demix, demix_pytorch_optimized, denormalize_audio, normalize_audio
+from .demix import apply_tta, demix, demix_pytorch_optimized, demix_tta, denormalize_audio, normalize_audio
 
 
 def shorten_filename(filename, max_length=30):
@@ -63,13 +63,26 @@ def build_parser():
 
 def load_checkpoint_into(model, path, device):
     """inference_pytorch.py:326-369: accept {'state_dict'|'model'|'state': ...} or a bare state_dict, strict=False."""
-    checkpoint = torch.load(path, map_location='cpu', weights_only=False)
+    try:
+        checkpoint = torch.load(path, map_location='cpu', weights_only=True)
+    except Exception as e:
+        # community checkpoints sometimes pickle arbitrary objects; unpickling those executes code, so it is opt-in
+        if os.environ.get('SESA_ALLOW_UNSAFE_CHECKPOINT') != '1':
+            raise RuntimeError(f'{path} is not a plain tensor checkpoint ({type(e).__name__}: {e}); set '
+                               'SESA_ALLOW_UNSAFE_CHECKPOINT=1 to unpickle it like the reference does '
+                               '(this runs code stored in the file)')
+        checkpoint = torch.load(path, map_location='cpu', weights_only=False)
     if isinstance(checkpoint, dict):
         for key in ('state_dict', 'model', 'state'):
             if key in checkpoint:
                 checkpoint = checkpoint[key]
                 break
-    model.load_state_dict(checkpoint, strict=False)
+    missing, unexpected = model.load_state_dict(checkpoint, strict=False)
+    matched = len(model.state_dict()) - len(missing)
+    print(f"Checkpoint keys: {matched} loaded, {len(missing)} missing, {len(unexpected)} unexpected")
+    if matched == 0:
+        raise RuntimeError(f'no key of {path} matches the {type(model).__name__} state_dict layout '
+                           '(wrong --model_type or config for this checkpoint?)')
 
 
 def _phase_remix(config, model, args, device, mix_orig, estimates, instruments):
@@ -116,9 +129,13 @@ def run_folder(backend, args, config, device, model=None):
         norm_params = None
         if 'normalize' in config.inference and config.inference['normalize'] is True:
             mix, norm_params = normalize_audio(mix)
-        waveforms_orig = demix_pytorch_optimized(config, backend, mix, device, pbar=detailed_pbar)
         if args.use_tta and model is not None:
-            waveforms_orig = apply_tta(config, model, mix, waveforms_orig, device, args.model_type)
+            # demix + apply_tta (:226-229) as one engine run over the three mixes; same stdout protocol
+            waveforms_orig = demix_tta(config, model, mix, device, args.model_type,
+                                       progress=lambda p: print(f"[SESA_PROGRESS]{p}", flush=True))
+            print("[SESA_PROGRESS]100", flush=True)
+        else:
+            waveforms_orig = demix_pytorch_optimized(config, backend, mix, device, pbar=detailed_pbar)
         if args.demud_phaseremix_inst and model is not None:
             instruments.append('instrumental_phaseremix')
             waveforms_orig['instrumental_phaseremix'] = _phase_remix(

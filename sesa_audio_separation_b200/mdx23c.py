@@ -309,11 +309,11 @@ class TFC_TDF_net(KernelModule):
         steps.append(lambda: call('sesa_mdx_unpack', _ptr(yout), B, T, self.fs, self.k, C2, self.num_target_instruments, Ffull,
                                   _ptr(ospec), _stream()))
         ws.update(steps=steps, keep=keep, ospec=ospec, env=env, out_len=out_len)
-        self._ws = {key: ws}
+        self._keep_workspace(key, ws)
         return ws
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x):
+    def forward(self, x, out=None):
         if not isinstance(x, torch.Tensor) or x.device.type != 'cuda':
             raise _lib.SesaError('forward() needs a CUDA tensor; there is no CPU path')
         B, C, L = x.shape
@@ -330,7 +330,11 @@ class TFC_TDF_net(KernelModule):
         for step in ws['steps']:
             step()
         nt = self.num_target_instruments
-        out = torch.empty(B, nt, C, ws['out_len'], device=audio.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(B, nt, C, ws['out_len'], device=audio.device, dtype=torch.float32)
+        else:
+            assert out.is_contiguous() and out.numel() == B * nt * C * ws['out_len']
+            out = out.view(B, nt, C, ws['out_len'])
         call('sesa_mask_istft', _ptr(ws['ospec']), None, None, None, _ptr(out), _ptr(prep['window']), _ptr(ws['env']),
              _ptr(prep['twiddle']), B, nt, C, self.n_fft, self.hop, T, ws['out_len'], 2, 0, st)
         return out[:, 0] if nt == 1 else out

@@ -31,6 +31,18 @@ class KernelModule:
             raise ValueError(kind)
         self._params[name] = t
 
+    # -- per-input-shape workspaces
+    WORKSPACE_SLOTS = 2   # the full engine batch and a track's ragged tail batch: neither is rebuilt per track
+
+    def _keep_workspace(self, key, ws):
+        """Remember ``ws`` for input shape ``key``, evicting the least recently built one beyond WORKSPACE_SLOTS (every
+        workspace holds multi-GB activation buffers and host-encoded TMA tables, so rebuilding one per launch is the
+        expensive thing to avoid and holding many is the other)."""
+        self._ws.pop(key, None)
+        while len(self._ws) >= self.WORKSPACE_SLOTS:
+            self._ws.pop(next(iter(self._ws)))
+        self._ws[key] = ws
+
     # -- nn.Module-like surface
     def state_dict(self):
         return OrderedDict((k, v) for k, v in self._params.items())

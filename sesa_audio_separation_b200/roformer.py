@@ -263,7 +263,9 @@ class _RoformerBase(KernelModule):
     def _workspace(self, B, L):
         key = (B, L)
         if key in self._ws:
-            return self._ws[key]
+            ws = self._ws.pop(key)          # most recently used last
+            self._ws[key] = ws
+            return ws
         prep, dev = self._prepared, self._device
         T = 1 + L // self.hop
         F = self.n_fft // 2 + 1
@@ -277,16 +279,30 @@ class _RoformerBase(KernelModule):
         ws = dict(T=T, F=F, M=M, out_len=out_len, ftot=ftot)
         ws['spec'] = torch.empty(B * T, F * C * 2, **f32)
         ws['x'] = torch.empty(M, D, **f32)
-        ws['qkv'] = torch.empty(M, self.ld_qkv, **f32)
-        ws['ao'] = torch.empty(M, self.inner, **f32)
-        ws['h'] = torch.empty(M, 4 * D, **f32)
-        ws['mh'] = [torch.empty(self.num_stems * nb, B * T, hidden, **f32)
-                    for _ in range(min(2, self.n_mask_linears - 1))]
         ws['mask'] = torch.empty(self.num_stems, B * T, ftot, **f32)
         ws['env'] = _istft_envelope(prep['window_cpu'], self.n_fft, self.hop, T, out_len).to(dev)
         if self.skip_connection:
             ws['store'] = [torch.empty(M, D, **f32) for _ in range(self.depth)]
         feat = self._features_buffer(ws, B, T)
+        if self._tc:
+            self._workspace_tc(ws, prep, B, T)
+        else:
+            self._workspace_simt(ws, prep, B, T, feat)
+        self._keep_workspace(key, ws)
+        return ws
+
+    def _workspace_simt(self, ws, prep, B, T, feat):
+        """fp32 activation buffers and group tables of the 'fp32_simt' cross-check mode only (the tensor-core modes never
+        read them; for the 4-stem Mel model they would be ~10 GB of dead memory)."""
+        dev = self._device
+        nb, D, M, ftot = self.num_bands, self.dim, ws['M'], ws['ftot']
+        hidden = D * self.mlp_expansion_factor
+        f32 = dict(device=dev, dtype=torch.float32)
+        ws['qkv'] = torch.empty(M, self.ld_qkv, **f32)
+        ws['ao'] = torch.empty(M, self.inner, **f32)
+        ws['h'] = torch.empty(M, 4 * D, **f32)
+        ws['mh'] = [torch.empty(self.num_stems * nb, B * T, hidden, **f32)
+                    for _ in range(min(2, self.n_mask_linears - 1))]
         # grouped GEMM tables
         offs = np.concatenate([[0], np.cumsum(self.dim_inputs)]).astype(np.int64)
         recs = []
@@ -331,10 +347,6 @@ class _RoformerBase(KernelModule):
                         ff2=single(ws['h'], s['w2'], s['b2'], ws['x'], M, D, 4 * D, 4 * D, D)))
                 gp.append(gs)
             ws['g_layers'].append(gp)
-        if self._tc:
-            self._workspace_tc(ws, prep, B, T)
-        self._ws = {key: ws}   # keep one workspace alive
-        return ws
 
     def _workspace_tc(self, ws, prep, B, T):
         """Plane buffers and TMA tables of the tensor-core path (built once per batch shape)."""
@@ -441,7 +453,7 @@ class _RoformerBase(KernelModule):
             pos_div, pos_mod = 1, nb
         nsplit = 3 if self.precision == 'fp32' else 1
         npl = 2 if nsplit == 3 else 1      # bf16 mode never reads the lo planes: do not write them either
-        for si, (s, g) in enumerate(zip(tr['subs'], gl)):
+        for si, (s, g) in enumerate(zip(tr['subs'], gl or [None] * len(tr['subs']))):
             rot = self._rot_table(prep, s['freqs'], seq_len)
             if self._tc:
                 t = tgl[si]
@@ -498,7 +510,7 @@ class _RoformerBase(KernelModule):
             ws['t_bandsplit'].run(_epilogue(), nsplit, 2 if nsplit == 3 else 1)
         else:
             self._gemm(ws['g_bandsplit'], _epilogue(rownorm=1))
-        for i, (pair, gp) in enumerate(zip(prep['layers'], ws['g_layers'])):
+        for i, (pair, gp) in enumerate(zip(prep['layers'], ws.get('g_layers') or [(None, None)] * self.depth)):
             if self.skip_connection:
                 for j in range(i):
                     call('sesa_add_inplace', _ptr(ws['x']), _ptr(ws['store'][j]), ws['x'].numel(), st)

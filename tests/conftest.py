@@ -48,3 +48,25 @@ def max_rel(ref, est):
     ref = np.asarray(ref, dtype=np.float64)
     est = np.asarray(est, dtype=np.float64)
     return np.abs(ref - est).max() / max(np.abs(ref).max(), 1e-300)
+
+
+def max_rel_framewise(ref, est, frame=4096):
+    """The stricter reading of 'max relative error': max over frames of (max |ref-est| in the frame) / (max |ref| in the
+    frame), frames of ``frame`` samples along the last axis.  A frame whose reference peak is below 1e-3 of the global
+    peak is normalised by that floor instead (a silent frame has no meaningful relative error)."""
+    ref = np.asarray(ref, dtype=np.float64)
+    est = np.asarray(est, dtype=np.float64)
+    n = ref.shape[-1] // frame * frame
+    if n == 0:
+        return max_rel(ref, est)
+    r = np.abs(ref[..., :n]).reshape(*ref.shape[:-1], -1, frame).max(-1)
+    d = np.abs(ref[..., :n] - est[..., :n]).reshape(*ref.shape[:-1], -1, frame).max(-1)
+    floor = 1e-3 * max(np.abs(ref).max(), 1e-300)
+    return float((d / np.maximum(r, floor)).max())
+
+
+def parity_report(label, ref, est):
+    """Prints and returns (global max-rel, frame-wise max-rel, SNR dB)."""
+    g, f, s = max_rel(ref, est), max_rel_framewise(ref, est), snr_db(ref, est)
+    print(f'{label}: max_rel {g:.3e} (global), {f:.3e} (per 4096-sample frame), snr {s:.1f} dB')
+    return g, f, s

@@ -610,3 +610,126 @@ def test_overlap_add_region_kernel_is_bit_identical_to_the_scalar_gather(lib, le
         cnt[s:s + n] += w[:n]
     ref = torch.nan_to_num((res / cnt)[:, crop:crop + length], nan=0.0)
     assert torch.equal(ref, b)
+
+
+@pytest.mark.parametrize('length,L,ov,bs,nc', [(4000, 1000, 1, 1, 2), (40000, 4000, 4, 2, 2), (40004, 4000, 4, 1, 1), (52000, 8000, 2, 3, 4),
+                                               (30011, 1001, 3, 2, 2), (9999, 1000, 8, 4, 3), (300, 1000, 4, 2, 2),
+                                               (60000, 1600, 16, 2, 1)])
+def test_overlap_accumulate_streams_to_the_same_bits(lib, length, L, ov, bs, nc):
+    """sesa_overlap_accumulate (the product path: one call per engine batch, running sums continued in `partial`) is
+    bit-identical to the one-shot gather sesa_overlap_add for every batching, vectorised and scalar geometries, partial
+    slabs and output windows that start mid-track, and never reads `partial` before writing it (NaN-filled here)."""
+    from sesa_audio_separation_b200.plan import make_plan, windowing_array
+    dev = 'cuda'
+    plan = make_plan(length, L, ov, bs)
+    g = torch.Generator(device=dev).manual_seed(length + L + ov)
+    y = torch.randn(plan.n_chunks, nc, L, device=dev, generator=g)
+    starts = torch.tensor(plan.starts, dtype=torch.int64, device=dev)
+    lens = torch.tensor(plan.lens, dtype=torch.int64, device=dev)
+    kinds = torch.tensor(plan.kinds, dtype=torch.int32, device=dev)
+    window = windowing_array(L, plan.fade).to(dev)
+    crop = plan.border if plan.pad else 0
+    ref = torch.full((nc, length), 7.0, device=dev)
+    counter = torch.empty(plan.padded, device=dev)
+    lib.call('sesa_overlap_add', P(y), P(starts), P(lens), P(kinds), plan.n_chunks, plan.step, L, plan.fade, P(window), 1, nc,
+             plan.padded, crop, length, P(ref), P(counter), S())
+    span = -(-L // plan.step)
+    ld = (length + 3) // 4 * 4
+    for eb in (1, 3, plan.n_chunks):
+        out = torch.full((nc, ld), float('nan'), device=dev)
+        partial = torch.full((nc, (plan.padded + 3) // 4 * 4 + 4), float('nan'), device=dev)
+        for k in range(0, plan.n_chunks, eb):
+            nb = min(eb, plan.n_chunks - k)
+            lib.call('sesa_overlap_accumulate', P(y[k:k + nb]), k, nb, P(starts), P(lens), P(kinds), plan.n_chunks, plan.step, L,
+                     plan.fade, P(window), 1, nc, plan.padded, k, k + nb + span - 1, P(partial), partial.shape[1], 0, crop,
+                     length, P(out), ld, 0, length, S())
+        torch.cuda.synchronize()
+        assert torch.equal(out[:, :length], ref), (eb, float((out[:, :length] - ref).abs().max()))
+    # a shard's view: chunks [lo, n) only, partial slab and output window starting at the shard's first region, the
+    # earlier chunks' raw sums handed in as the halo
+    if plan.n_chunks >= 2 * span and plan.step % 4 == 0:
+        lo = plan.n_chunks // 2
+        p0 = plan.starts[lo]
+        part_a = torch.full((nc, (plan.padded + 3) // 4 * 4 + 4), float('nan'), device=dev)
+        out_a = torch.full((nc, ld), float('nan'), device=dev)
+        lib.call('sesa_overlap_accumulate', P(y[:lo]), 0, lo, P(starts), P(lens), P(kinds), plan.n_chunks, plan.step, L, plan.fade,
+                 P(window), 1, nc, plan.padded, 0, lo + span - 1, P(part_a), part_a.shape[1], 0, crop, length, P(out_a), ld, 0,
+                 length, S())
+        halo_p1 = min(plan.padded, (lo + span - 1) * plan.step)
+        part_b = torch.full((nc, (plan.padded - p0 + 3) // 4 * 4 + 4), float('nan'), device=dev)
+        part_b[:, :halo_p1 - p0] = part_a[:, p0:halo_p1]
+        q0 = max(p0 - crop, 0)
+        out_b = torch.full((nc, (length - q0 + 3) // 4 * 4), float('nan'), device=dev)
+        lib.call('sesa_overlap_accumulate', P(y[lo:]), lo, plan.n_chunks - lo, P(starts), P(lens), P(kinds), plan.n_chunks,
+                 plan.step, L, plan.fade, P(window), 1, nc, plan.padded, lo, plan.n_chunks + span, P(part_b), part_b.shape[1], p0,
+                 crop, length, P(out_b), out_b.shape[1], q0, out_b.shape[1], S())
+        torch.cuda.synchronize()
+        assert torch.equal(out_a[:, :q0], ref[:, :q0])
+        assert torch.equal(out_b[:, :length - q0], ref[:, q0:])
+
+
+def test_pad_reflect_slice_equals_the_full_pad(lib):
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(3)
+    C, length, border = 2, 5003, 750
+    mix = torch.randn(C, length, device=dev, generator=g)
+    full = torch.empty(C, length + 2 * border, device=dev)
+    lib.call('sesa_pad_reflect', P(mix), P(full), C, length, border, border, S())
+    assert torch.equal(full, torch.nn.functional.pad(mix[None], (border, border), mode='reflect')[0])
+    for p0, p1 in ((0, 1000), (0, 2100), (1000, 3000), (4500, length + 2 * border), (5500, length + 2 * border), (0, length + 2 * border)):
+        idx = [abs(j) if j < length else 2 * (length - 1) - j for j in (p0 - border, p1 - 1 - border)]
+        m0, m1 = min(idx), max(idx)
+        if p0 - border < 0:
+            m0 = 0
+        if p1 - 1 - border >= length:
+            m1 = length - 1
+        win = mix[:, m0:m1 + 1].contiguous()
+        out = torch.empty(C, p1 - p0, device=dev)
+        lib.call('sesa_pad_reflect_slice', P(win), win.shape[1], m0, P(out), C, length, border, p0, p1 - p0, S())
+        assert torch.equal(out, full[:, p0:p1]), (p0, p1)
+    with pytest.raises(lib.SesaError):      # a window that does not hold the needed samples is refused, not read out of bounds
+        win = mix[:, 100:200].contiguous()
+        lib.call('sesa_pad_reflect_slice', P(win), 100, 100, P(out), C, length, border, 0, 1000, S())
+
+
+def test_tta_kernels_match_numpy_statement(lib):
+    """utils.apply_tta's arithmetic (utils.py:271-290) on the device: augmented mixes and the += / -= / /= 3 sequence."""
+    dev = 'cuda'
+    rng = np.random.default_rng(1)
+    mix = rng.standard_normal((2, 12345)).astype(np.float32)
+    m = torch.from_numpy(mix).to(dev)
+    sw, ng = torch.empty_like(m), torch.empty_like(m)
+    lib.call('sesa_tta_variants', P(m), P(sw), P(ng), 2, mix.shape[1], S())
+    assert np.array_equal(sw.cpu().numpy(), mix[::-1].copy()) and np.array_equal(ng.cpu().numpy(), -1.0 * mix.copy())
+    est = [rng.standard_normal((3, 2, 12345)).astype(np.float32) for _ in range(3)]
+    want = est[0].copy()
+    for n in range(3):
+        want[n] += est[1][n][::-1].copy()
+        want[n] -= est[2][n]
+        want[n] /= 3
+    d = [torch.from_numpy(e).to(dev) for e in est]
+    out = torch.empty_like(d[0])
+    lib.call('sesa_tta_combine', P(d[0]), P(d[1]), P(d[2]), P(out), 3, 2, 12345, S())
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_ensemble_wave_kernel_matches_numpy_on_float64(lib):
+    """ensemble.py:172-183 on stems resident on the GPU: float64 accumulation in input order = numpy on the float64
+    buffers the reference reads; the float32 result is the correctly rounded float64 one."""
+    import sesa_audio_separation_b200 as sesa
+    rng = np.random.default_rng(2)
+    stems = [(rng.standard_normal((2, 50001)) * 0.3).astype(np.float32) for _ in range(4)]
+    dev_stems = [torch.from_numpy(s).cuda() for s in stems]
+    f64 = np.stack([s.astype(np.float64) for s in stems], 0)
+    for n in (3, 4):
+        got = sesa.ensemble_waveforms(dev_stems[:n], 'avg_wave').cpu().numpy()
+        assert np.array_equal(got, np.mean(f64[:n], axis=0).astype(np.float32))
+        w = [1.0, 2.0, 0.5, 3.0][:n]
+        w32 = np.array(w, dtype=np.float32)
+        w32 /= w32.sum()
+        got = sesa.ensemble_waveforms(dev_stems[:n], 'avg_wave', w).cpu().numpy()
+        assert np.array_equal(got, np.average(f64[:n], axis=0, weights=w32).astype(np.float32))
+        assert np.array_equal(sesa.ensemble_waveforms(dev_stems[:n], 'median_wave').cpu().numpy(),
+                              np.median(f64[:n], axis=0).astype(np.float32))
+        assert np.array_equal(sesa.ensemble_waveforms(dev_stems[:n], 'max_wave').cpu().numpy(), np.max(f64[:n], axis=0).astype(np.float32))
+        assert np.array_equal(sesa.ensemble_waveforms(dev_stems[:n], 'min_wave').cpu().numpy(), np.min(f64[:n], axis=0).astype(np.float32))

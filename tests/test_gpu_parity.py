@@ -5,9 +5,9 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden, max_rel, snr_db
+from conftest import golden, max_rel, parity_report, snr_db
 from oracle import demix as odemix
-from oracle.cases import CASES, DEMIX_IDENTITY_CASES, DEMIX_MODEL_CASES, make_input
+from oracle.cases import CASES, DEMIX_IDENTITY_CASES, DEMIX_MODEL_CASES, FLOW_CASES, make_input
 from oracle.weights import fill_state_dict, synth_mix
 
 pytestmark = pytest.mark.gpu
@@ -269,24 +269,81 @@ def test_demix_mdx23c_vs_oracle():
         assert snr_db(ref[i], res[k]) >= FP32_SNR_DB
 
 
-def test_apply_tta_matches_reference_formula():
-    """utils.apply_tta (utils.py:241-292): (orig + swap(demix(swap(mix))) - demix(-mix)) / 3 in the reference's order."""
+def _flow_config(fc):
     import sesa_audio_separation_b200 as sesa
-    case = CASES['bs_small']
+    return sesa.ConfigDict(dict(audio=dict(chunk_size=fc['chunk_size'], sample_rate=44100, num_channels=2),
+                                inference=dict(num_overlap=fc['num_overlap'], batch_size=fc['batch_size'],
+                                               **({'normalize': True} if fc['normalize'] else {})),
+                                training=dict(instruments=fc['instruments'], target_instrument=fc['target'])))
+
+
+@pytest.mark.parametrize('name', list(FLOW_CASES))
+def test_per_file_flow_matches_reference_golden(tmp_path, name):
+    """normalize -> demix -> TTA -> DemudPhaseRemix -> instrumental -> denormalize (inference_pytorch.py:219-260) through
+    the product's run_folder against the arrays the UNMODIFIED reference flow wrote (oracle/make_golden.py run_flows):
+    covers utils.normalize_audio / denormalize_audio / apply_tta and both DemudPhaseRemix branches."""
+    import argparse
+    import sesa_audio_separation_b200 as sesa
+    from sesa_audio_separation_b200.audio_io import load_audio, write_audio
+    from sesa_audio_separation_b200.inference import run_folder
+    fc = FLOW_CASES[name]
+    case = CASES[fc['model']]
     model, _ = build(case)
-    L = 441 * 40
-    cfg = sesa.ConfigDict(dict(audio=dict(chunk_size=L), inference=dict(num_overlap=2, batch_size=1),
-                               training=dict(instruments=['vocals', 'other'], target_instrument='vocals')))
-    mix = synth_mix(L * 2 + 100, 2, seed=61)
-    base = sesa.demix(cfg, model, mix, 'cuda', 'bs_roformer')
-    a = sesa.demix(cfg, model, mix[::-1].copy(), 'cuda', 'bs_roformer')['vocals']
-    b = sesa.demix(cfg, model, -1.0 * mix.copy(), 'cuda', 'bs_roformer')['vocals']
-    want = base['vocals'].copy()
-    want += a[::-1].copy()
-    want -= b
-    want /= 3
-    got = sesa.apply_tta(cfg, model, mix, {k: v.copy() for k, v in base.items()}, 'cuda', 'bs_roformer')
-    assert np.array_equal(got['vocals'], want)
+    config = _flow_config(fc)
+    mix = synth_mix(fc['length'], 2, seed=fc['seed'])
+    indir, outdir = tmp_path / 'in', tmp_path / 'out'
+    indir.mkdir()
+    write_audio(str(indir / 'song.wav'), mix.T, 44100, subtype='FLOAT')
+    args = argparse.Namespace(input_folder=str(indir), store_dir=str(outdir), disable_detailed_pbar=True,
+                              use_tta=fc['use_tta'], demud_phaseremix_inst=fc['demud'],
+                              extract_instrumental=fc['extract_instrumental'], model_type=case['kind'],
+                              export_format='wav FLOAT', flac_file=False, pcm_type='PCM_24')
+    backend = sesa.create_inference_session(model, device='cuda', optimize_mode='default', enable_amp=False)
+    written = run_folder(backend, args, config, 'cuda', model=model)
+    g = golden(name)
+    assert sorted(os.path.basename(w) for w in written) == sorted(g.keys())
+    for fn in g.keys():
+        got, _ = load_audio(str(outdir / fn), 44100)
+        assert got.shape == g[fn].shape
+        gl, fr, snr = parity_report(f'{name} {fn}', g[fn], got)
+        assert gl <= FP32_MAX_REL and snr >= FP32_SNR_DB
+
+
+def test_apply_tta_matches_reference_golden_and_fused_run():
+    """utils.apply_tta (utils.py:241-292) against the reference golden of the flow that ends with TTA-only arithmetic
+    (flow_bs_norm_tta_demud's vocals = denormalize(apply_tta(demix(normalize(mix))))), and the three forms the product
+    offers — demix()+apply_tta() (two engine runs), demix_tta() (one engine run, combined on the device) — are
+    bit-identical to each other."""
+    import sesa_audio_separation_b200 as sesa
+    fc = FLOW_CASES['flow_bs_norm_tta_demud']
+    case = CASES[fc['model']]
+    model, _ = build(case)
+    config = _flow_config(fc)
+    mix = synth_mix(fc['length'], 2, seed=fc['seed'])
+    nmix, params = sesa.normalize_audio(mix)
+    base = sesa.demix(config, model, nmix, 'cuda', case['kind'])
+    two_step = sesa.apply_tta(config, model, nmix, {k: v.copy() for k, v in base.items()}, 'cuda', case['kind'])
+    fused = sesa.demix_tta(config, model, nmix, 'cuda', case['kind'], engine_batch=3)
+    assert np.array_equal(two_step['vocals'], fused['vocals'])
+    ref = golden('flow_bs_norm_tta_demud')['song.wav_vocals.wav']
+    got = sesa.denormalize_audio(fused['vocals'], params)
+    gl, fr, snr = parity_report('apply_tta vs reference', ref, got)
+    assert gl <= FP32_MAX_REL and snr >= FP32_SNR_DB
+    # and the oracle's restatement of apply_tta applied to the product's three demix results gives the same bits
+    ora = odemix.apply_tta(nmix, lambda m: sesa.demix(config, model, m, 'cuda', case['kind']), {k: v.copy() for k, v in base.items()})
+    assert np.array_equal(ora['vocals'], fused['vocals'])
+
+
+def test_normalize_denormalize_match_reference_statements():
+    """utils.normalize_audio / denormalize_audio (utils.py:199-238) are host numpy in the reference and in the product:
+    same bits as the oracle's restatement, and the full normalize -> demix -> denormalize flow is pinned by the
+    'flow_bs_norm_only' reference golden above."""
+    import sesa_audio_separation_b200 as sesa
+    mix = synth_mix(30000, 2, seed=5) * 0.3 + 0.05
+    a, pa = sesa.normalize_audio(mix)
+    b, pb = odemix.normalize_audio(mix)
+    assert np.array_equal(a, b) and pa['mean'] == pb['mean'] and pa['std'] == pb['std']
+    assert np.array_equal(sesa.denormalize_audio(a, pa), odemix.denormalize_audio(b, pb))
 
 
 def test_hop512_config_and_odd_lengths_vs_oracle():
@@ -355,3 +412,100 @@ def test_full_size_bs_roformer_forward_is_batch_invariant_and_reproducible():
     for i in (0, 2):
         yi = model(x[i:i + 1])
         assert torch.equal(yi[0], y[i]), (i, float((yi[0] - y[i]).abs().max()))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Full BASELINE configurations end to end: the real model through sesa.demix() over a multi-chunk track (border pad,
+# ragged tail chunks, several engine batches) against oracle.demix driving the oracle forward in true fp32.
+def _oracle_on_gpu():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def _check_stems(label, names, ref, res):
+    for i, k in enumerate(names):
+        assert res[k].shape == ref[i].shape
+        gl, fr, snr = parity_report(f'{label} {k}', ref[i], res[k])
+        assert gl <= FP32_MAX_REL and snr >= FP32_SNR_DB
+        assert fr <= 3 * FP32_MAX_REL     # the stricter per-frame reading, with its own (looser) bound
+
+
+def test_full_config_c2_bs_roformer_demix_vs_oracle():
+    """BASELINE C2: BS-RoFormer dim 512 depth 12 (159.8 M parameters), chunk 352 800, overlap 4, on a 37-s track ->
+    22 chunks incl. the reflect-padded borders and the three ragged tail chunks (reflect / zero / zero padded),
+    6 engine batches; oracle = oracle.demix + bs_roformer_forward on CUDA in fp32 (TF32 off)."""
+    import sesa_audio_separation_b200 as sesa
+    from conftest import ROOT
+    from oracle import roformer as orof
+    _oracle_on_gpu()
+    model, config = sesa.get_model_from_config('bs_roformer', os.path.join(ROOT, 'configs', 'config_bs_roformer_vocals.yaml'))
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=3)
+    model.load_state_dict(sd)
+    model.eval().to('cuda')
+    L, ov, bs = int(config.audio.chunk_size), int(config.inference.num_overlap), int(config.inference.batch_size)
+    length = 37 * 44100 + 1234
+    mix = synth_mix(length, 2, seed=91)
+    eng = sesa.DemixEngine(config, model, 'cuda', engine_batch=4)
+    est = eng.run(mix)
+    assert eng.plan.n_chunks >= 20 and eng.plan.pad and eng.plan.lens[-1] < L
+    mcfg = dict(config.model)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    with torch.inference_mode():
+        ref = odemix.demix(mix, lambda a: orof.bs_roformer_forward(sd_gpu, mcfg, a.cuda()).cpu(), L, ov, bs, 1)
+    _check_stems(f'C2 full config ({eng.plan.n_chunks} chunks)', ['vocals'], ref, {'vocals': est[0]})
+
+
+def test_full_config_c3_mel_4stem_demix_vs_oracle():
+    """BASELINE C3 model (Mel-Band-RoFormer 4 stems, 832.6 M parameters), chunk 352 800, overlap 2, on a 20-s track ->
+    7 chunks = 2 engine batches of 4 + 3; oracle on CUDA in fp32 with the exact real-view scatter (oracle/roformer.py),
+    its first chunk cross-checked against the pinned CPU oracle."""
+    import sesa_audio_separation_b200 as sesa
+    from conftest import ROOT
+    from oracle import roformer as orof
+    _oracle_on_gpu()
+    model, config = sesa.get_model_from_config('mel_band_roformer', os.path.join(ROOT, 'configs', 'config_mel_band_roformer_4stem.yaml'))
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=41)
+    model.load_state_dict(sd)
+    model.eval().to('cuda')
+    L, ov, bs = int(config.audio.chunk_size), int(config.inference.num_overlap), int(config.inference.batch_size)
+    length = 20 * 44100
+    mix = synth_mix(length, 2, seed=92)
+    eng = sesa.DemixEngine(config, model, 'cuda', engine_batch=4)
+    est = eng.run(mix)
+    assert eng.plan.n_chunks >= 5
+    mcfg = dict(config.model)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    with torch.inference_mode():
+        ref = odemix.demix(mix, lambda a: orof.mel_band_roformer_forward(sd_gpu, mcfg, a.cuda()).cpu(), L, ov, bs, 4)
+        x0 = torch.from_numpy(mix[:, :L].copy())[None]
+        torch.set_num_threads(os.cpu_count())
+        cpu0 = orof.mel_band_roformer_forward(sd, mcfg, x0).numpy()
+        gpu0 = orof.mel_band_roformer_forward(sd_gpu, mcfg, x0.cuda()).cpu().numpy()
+    print('oracle on CUDA vs pinned CPU oracle, one chunk: max_rel', max_rel(cpu0, gpu0))
+    assert max_rel(cpu0, gpu0) <= 2e-5
+    names = list(sesa.prefer_target_instrument(config))
+    _check_stems(f'C3 full config ({eng.plan.n_chunks} chunks)', names, ref, dict(zip(names, est)))
+
+
+def test_full_config_c1_mdx23c_30s_demix_vs_oracle():
+    """BASELINE C1: MDX23C vocals (112 M parameters), 30-s track, chunk 261 120, overlap 4 -> 27 chunks, the exact
+    configuration BASELINE.json names; oracle.demix + mdx23c_forward on CUDA in fp32."""
+    import sesa_audio_separation_b200 as sesa
+    from conftest import ROOT
+    from oracle import mdx23c as omdx
+    _oracle_on_gpu()
+    model, cfg = sesa.get_model_from_config('mdx23c', os.path.join(ROOT, 'configs', 'config_vocals_mdx23c.yaml'))
+    sd = fill_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=21)
+    model.load_state_dict(sd)
+    model.eval().to('cuda')
+    L, ov, bs = int(cfg.audio.chunk_size), int(cfg.inference.num_overlap), int(cfg.inference.batch_size)
+    mix = synth_mix(30 * 44100, 2, seed=93)
+    eng = sesa.DemixEngine(cfg, model, 'cuda', engine_batch=4)
+    est = eng.run(mix)
+    assert eng.plan.n_chunks == 27
+    ocfg = dict(audio=dict(cfg.audio), model=dict(cfg.model), num_target_instruments=2)
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    with torch.inference_mode():
+        ref = odemix.demix(mix, lambda a: omdx.mdx23c_forward(sd_gpu, ocfg, a.cuda()).cpu(), L, ov, bs, 2)
+    names = list(sesa.prefer_target_instrument(cfg))
+    _check_stems('C1 full config (27 chunks)', names, ref, dict(zip(names, est)))

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/sesa_b200.h but not exported'
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.sesa_abi_version() == 2
+    assert lib.sesa_abi_version() == 3
 
 
 def test_plan_matches_oracle_schedule():
@@ -142,9 +142,9 @@ def test_audio_io_roundtrip_and_ensemble(tmp_path):
     assert np.allclose(ensemble_waveforms(stems, 'avg_wave', [1, 2, 3]), np.average(stems, axis=0, weights=[1, 2, 3]))
     assert np.array_equal(ensemble_waveforms(stems, 'median_wave'), np.median(stems, axis=0))
     assert np.array_equal(ensemble_waveforms(stems, 'max_wave'), np.max(stems, axis=0))
-    t = [torch.from_numpy(s) for s in stems + [x * 2]]
-    assert np.allclose(ensemble_waveforms(t, 'median_wave').numpy(), np.median([s.numpy() for s in t], axis=0))
-    assert np.allclose(ensemble_waveforms(t, 'avg_wave', [1, 1, 2, 4]).numpy(), np.average([s.numpy() for s in t], axis=0, weights=[1, 1, 2, 4]), atol=1e-7)
+    # torch inputs mean "stems still on the GPU" (sesa_ensemble_wave, tests/test_gpu_kernels.py); CPU tensors are refused
+    with pytest.raises(RuntimeError):
+        ensemble_waveforms([torch.from_numpy(s) for s in stems], 'avg_wave')
     files = []
     for i, s in enumerate(stems):
         f = str(tmp_path / f's{i}.wav')

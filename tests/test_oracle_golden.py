@@ -7,7 +7,8 @@ from conftest import golden, max_rel, snr_db
 from oracle import demix as odemix
 from oracle import mdx23c as omdx
 from oracle import roformer as orof
-from oracle.cases import CASES, DEMIX_IDENTITY_CASES, DEMIX_MODEL_CASES, make_input
+from oracle import flow as oflow
+from oracle.cases import CASES, DEMIX_IDENTITY_CASES, DEMIX_MODEL_CASES, FLOW_CASES, make_input
 from oracle.weights import fill_state_dict, synth_mix
 
 
@@ -72,3 +73,30 @@ def test_demix_model_matches_reference(manifest, name):
         assert e.shape == g[k].shape
         assert max_rel(g[k], e) <= 2e-5
         assert snr_db(g[k], e) >= 90
+
+
+@pytest.mark.parametrize('name', list(FLOW_CASES))
+def test_flow_matches_reference(manifest, name):
+    """normalize -> demix -> TTA -> DemudPhaseRemix -> instrumental -> denormalize: the oracle's restatement
+    (oracle/flow.py) against what the unmodified inference_pytorch.run_folder_pytorch_optimized wrote."""
+    fc = FLOW_CASES[name]
+    case = CASES[fc['model']]
+    sd = seeded_sd(manifest, fc['model'])
+    instr = odemix.prefer_target_instrument(dict(instruments=fc['instruments'], target_instrument=fc['target']))
+    mix = synth_mix(fc['length'], 2, seed=fc['seed'])
+
+    def demix_fn(m):
+        with torch.inference_mode():
+            est = odemix.demix(m, lambda a: oracle_forward(case, sd, a), fc['chunk_size'], fc['num_overlap'],
+                               fc['batch_size'], len(instr))
+        return {k: e for k, e in zip(instr, est)}
+    out, names = oflow.separate_track(mix, demix_fn, fc['instruments'] if fc['target'] is None else instr,
+                                      normalize=fc['normalize'], use_tta=fc['use_tta'], demud=fc['demud'],
+                                      extract_instrumental=fc['extract_instrumental'])
+    g = golden(name)
+    assert sorted(f'song.wav_{n}.wav' for n in names) == sorted(g.keys())
+    for n in names:
+        ref = g[f'song.wav_{n}.wav']
+        assert out[n].shape == ref.shape
+        assert max_rel(ref, out[n]) <= 2e-5, (n, max_rel(ref, out[n]))
+        assert snr_db(ref, out[n]) >= 90, (n, snr_db(ref, out[n]))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Micro-benchmark of the HBM-bound kernels of the hot path at the BASELINE C2 shapes (BS-RoFormer, n_fft 2048,
-hop 441, chunk 352 800, stereo): STFT, fused mask+iSTFT, chunk framing and the demix overlap-add.  CUDA-event timing on
+hop 441, chunk 352 800, stereo): STFT, fused mask+iSTFT, chunk framing and the streamed demix overlap-add.  CUDA-event timing on
 the launching stream; L2 is flushed between repetitions by writing a 512 MB buffer.  Bytes are the ALGORITHMIC bytes of
 SURVEY 8d (each tensor read or written once).  Used for the ncu captures under profiles/."""
 import argparse
@@ -80,14 +80,20 @@ def measure(chunks=4, reps=7, stems=1, seconds=180.0, only='', verbose=False):
     modes = torch.tensor(plan.modes, dtype=torch.int32).to(dev)
     kinds = torch.tensor(plan.kinds, dtype=torch.int32).to(dev)
     if sel is None or 'ola' in sel:
-        chunk_out = torch.randn(plan.n_chunks, NS, C, L, device=dev, generator=g)
-        result = torch.empty(NS, C, length, device=dev)
+        # the streamed overlap-add of the product path: one engine batch (B chunks, mid-track) folded into the running sums
+        y = torch.randn(B, NS, C, L, device=dev, generator=g)
+        result = torch.empty(NS * C, (length + 3) // 4 * 4, device=dev)
+        partial = torch.zeros(NS * C, (plan.padded + 3) // 4 * 4 + 4, device=dev)
         window = windowing_array(L, plan.fade).to(dev)
         crop = plan.border if plan.pad else 0
-        ms = timed(lambda: _lib.call('sesa_overlap_add', P(chunk_out), P(starts), P(lens), P(kinds), plan.n_chunks, plan.step, L,
-                                     plan.fade, P(window), NS, C, plan.padded, crop, length, P(result), None, S), reps, flush)
-        report('overlap_add', ms, 4 * NS * C * (L * plan.n_chunks + length))
-        del chunk_out, result
+        span = -(-L // plan.step)
+        k0 = plan.n_chunks // 2
+        ms = timed(lambda: _lib.call('sesa_overlap_accumulate', P(y), k0, B, P(starts), P(lens), P(kinds), plan.n_chunks, plan.step,
+                                     L, plan.fade, P(window), NS, C, plan.padded, k0, k0 + B + span - 1, P(partial),
+                                     partial.shape[1], 0, crop, length, P(result), result.shape[1], 0, length, S), reps, flush)
+        # chunk outputs read once, finished regions written once, the (span-1) open regions read and written back
+        report('overlap_add', ms, 4 * NS * C * (B * L + B * plan.step + 2 * (span - 1) * plan.step))
+        del y, result, partial
     if sel is None or 'frame' in sel:
         padded = torch.randn(C, plan.padded, device=dev, generator=g)
         chunks_t = torch.empty(B, C, L, device=dev)
