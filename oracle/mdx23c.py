@@ -10,6 +10,8 @@ plus act='relu' are restated.
 import torch
 import torch.nn.functional as F
 
+from .third_party import istft_exact
+
 
 def _norm(x, sd, p):
     """get_norm 'InstanceNorm' -> nn.InstanceNorm2d(c, affine=True) (:47-59): per (b,c) stats over
@@ -45,7 +47,7 @@ def stft_inv(x, n_fft, hop):
     x = torch.cat([x, torch.zeros([*batch_dims, c, n - f, t], device=x.device)], -2)
     x = x.reshape([*batch_dims, c // 2, 2, n, t]).reshape([-1, 2, n, t]).permute(0, 2, 3, 1)
     z = torch.complex(x[..., 0].contiguous(), x[..., 1].contiguous())
-    y = torch.istft(z, n_fft=n_fft, hop_length=hop, window=window, center=True)
+    y = istft_exact(z, n_fft=n_fft, hop_length=hop, window=window, center=True)
     return y.reshape([*batch_dims, 2, -1])
 
 

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .third_party import apply_rotary, mel as _mel
+from .third_party import apply_rotary, istft_exact, mel as _mel
 
 DEFAULT_FREQS_PER_BANDS = (  # models/bs_roformer/bs_roformer.py:315-324
     (2,) * 24 + (4,) * 12 + (12,) * 8 + (24,) * 8 + (48,) * 8 + (128, 129)
@@ -125,7 +125,7 @@ def _istft(spec, s, n_fft, hop, win_length, window, length):
     """bs_roformer.py:571-582: spec complex (b, n, f*s, t) -> (b, n, s, L)."""
     b, n, fs, t = spec.shape
     z = spec.reshape(b, n, fs // s, s, t).permute(0, 1, 3, 2, 4).reshape(b * n * s, fs // s, t)
-    y = torch.istft(z, n_fft=n_fft, hop_length=hop, win_length=win_length, normalized=False,
+    y = istft_exact(z, n_fft=n_fft, hop_length=hop, win_length=win_length, normalized=False,
                     window=window, return_complex=False, length=length)
     return y.reshape(b, n, s, -1)
 
@@ -209,14 +209,7 @@ def mel_band_roformer_forward(sd, cfg, raw_audio):
     masks = torch.view_as_complex(masks)
     spec = torch.view_as_complex(stft_repr.contiguous())[:, None]           # b 1 (f s) t
     idx = freq_indices[None, None, :, None].expand(b, num_stems, -1, t)
-    if spec.device.type == 'cpu':
-        summed = torch.zeros(b, num_stems, fs, t, dtype=spec.dtype, device=spec.device).scatter_add_(2, idx, masks)
-    else:
-        # torch's COMPLEX scatter_add_ on CUDA was measured to differ from its own CPU result by 6e-3 at full size
-        # (torch 2.11, B200; tools/debug_mel.py).  The same sum on the real view is exact on any device: every bin
-        # receives at most two addends (num_bands_per_freq <= 2) and a + b == b + a.
-        summed = torch.view_as_complex(torch.zeros(b, num_stems, fs, t, 2, dtype=raw_audio.dtype, device=spec.device)
-                                       .index_add_(2, freq_indices, torch.view_as_real(masks)))
+    summed = torch.zeros(b, num_stems, fs, t, dtype=spec.dtype, device=spec.device).scatter_add_(2, idx, masks)
     denom = nbpf.to(raw_audio.device).repeat_interleave(s)[:, None]          # '(f r) 1'
     spec = spec * (summed / denom.clamp(min=1e-8))
     y = _istft(spec, s, n_fft, hop, win, window, length)

@@ -89,3 +89,17 @@ def mel(*, sr, n_fft, n_mels=128, fmin=0.0, fmax=None, dtype=np.float32):
     enorm = 2.0 / (mel_f[2: n_mels + 2] - mel_f[:n_mels])
     weights *= enorm[:, np.newaxis]
     return weights
+
+
+def istft_exact(z, **kw):
+    """torch.istft evaluated where it is accurate.  Measured on B200 / torch 2.11 (tools/debug_c1.py, kept under
+    profiles/r2_torch_istft_cuda.md): on CUDA tensors torch.istft is exact for 1-2 signals but off by up to 1.6e-2 of the
+    peak for a batch of 8 signals and 7e-3 for 4, for any n_fft / hop / length, while torch.stft on CUDA and everything
+    else in the forward agree with the CPU to ~1e-6.  The CPU evaluation is the reference's own CPU path, so a CUDA
+    spectrogram is inverted on the CPU and the waveform handed back on its device."""
+    if z.device.type == 'cpu':
+        return torch.istft(z, **kw)
+    kw = dict(kw)
+    if kw.get('window') is not None:
+        kw['window'] = kw['window'].cpu()
+    return torch.istft(z.cpu(), **kw).to(z.device)

@@ -126,6 +126,15 @@ class DemixEngine:
              plan.step, self.chunk_size, plan.fade, _ptr(sch.window), n_inst, C, plan.padded, r0, r1, _ptr(partial),
              partial.shape[1], part_p0, crop, plan.length, _ptr(out), out.stride(0), out_q0, out_cols, _stream())
 
+    def _download(self, t):
+        """Device tensor -> numpy through page-locked memory (torch's caching host allocator recycles the block once the
+        caller drops the previous result, so steady-state runs pay no pinning cost) in ONE copy."""
+        t = t.contiguous()
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
+
     def _report(self, plan, k_done, state):
         if self.progress is None:
             return
@@ -195,6 +204,12 @@ class DemixEngine:
         tasks = [(v, k) for v in range(V) for k in range(plan.n_chunks)]
         state = [-1]
         t = 0
+        # to_host: finished regions of the result leave for (page-locked) host memory on a side stream while later
+        # batches are still being computed, so the device->host read costs no time after the last batch
+        sink = None
+        if to_host and V == 1:
+            sink = dict(host=torch.empty(rows, length, dtype=torch.float32, pin_memory=True), done=0,
+                        stream=self._side_stream(), crop=plan.border if plan.pad else 0)
         while t < len(tasks):
             batch = tasks[t:t + EB]
             nb = len(batch)
@@ -210,6 +225,8 @@ class DemixEngine:
             for v, k0, n, slot in segs:
                 self._accumulate(sch, y[slot:slot + n], k0, n, k0, k0 + n + span - 1, partial[v], 0, results[v], 0, length)
             t += nb
+            if sink is not None:
+                self._drain(sink, results[0], length if t >= len(tasks) else min(max(t * plan.step - sink['crop'], 0), length))
             self._report(plan, (t - 1) % plan.n_chunks + 1 if V == 1 else max(1, t * plan.n_chunks // len(tasks)), state)
         results = results[:, :, :length]
         if tta:
@@ -229,8 +246,30 @@ class DemixEngine:
                  L, plan.fade, _ptr(sch.window), n_inst, C, plan.padded, crop, 0, None, _ptr(counter), st)
         if not to_host:
             return (result, counter) if return_counter else result
-        est = result.cpu().numpy()
+        if sink is not None:
+            sink['stream'].synchronize()
+            est = sink['host'].numpy().reshape(n_inst, C, length)
+        else:
+            est = self._download(result)
         return (est, counter.cpu().numpy()) if return_counter else est
+
+    def _side_stream(self):
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._copy_stream
+
+    def _drain(self, sink, result_rows, upto):
+        """Queue the device->host copy of result samples [sink.done, upto) of every row behind the work issued so far."""
+        a, b = sink['done'], int(upto)
+        if b <= a:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(sink['stream']):
+            sink['stream'].wait_event(ev)
+            for row in range(result_rows.shape[0]):
+                sink['host'][row, a:b].copy_(result_rows[row, a:b], non_blocking=True)
+        sink['done'] = b
 
     # ------------------------------------------------------------------ chunk-range sharded
     def _run_sharded(self, mix, to_host):
@@ -338,7 +377,7 @@ class DemixEngine:
         if result is None:
             return None
         result = result[:, :length].reshape(n_inst, C, length)
-        return result.cpu().numpy() if to_host else result
+        return self._download(result) if to_host else result
 
     def timings(self):
         """Device-side milliseconds of the last sharded run on this rank (call after a synchronize)."""
