@@ -12,10 +12,10 @@ sharded result is bit-identical to the unsharded one.
 
 Schedule of one rank (``run_sharded_track``), built so that no rank ever waits for a neighbour's model passes:
 
-1. post the receive of the incoming halo;
-2. TAIL FIRST: run the model on the rank's LAST chunks (at least ``span - 1`` of them), fold them into the regions the
-   next rank owns (those depend on nothing else), and post the halo send at once — it crosses NVLink while every rank is
-   still busy with the rest of its range; the tail outputs are kept;
+1. TAIL FIRST: run the model on the rank's LAST chunks (at least ``span - 1`` of them) and fold them into the regions the
+   next rank owns (those depend on nothing else); the tail outputs are kept;
+2. ONE grouped exchange (ncclGroupStart / ncclSend to the next rank / ncclRecv from the previous rank / ncclGroupEnd):
+   the halos cross NVLink while every rank is still busy with the rest of its range;
 3. walk the remaining chunks in ascending engine batches, each folded into the running sums as soon as its forward is
    done (``sesa_overlap_accumulate``); the first fold continues from the received halo;
 4. fold the kept tail outputs into the rank's own regions (ascending order is preserved: they are its last chunks);
@@ -98,21 +98,21 @@ def run_sharded_track(plan, world, rank, ops, engine_batch, group=None, stats=No
     n_regions = -(-plan.padded // step)
     mark = getattr(ops, 'mark', lambda name: None)
 
-    halo, req_in = None, None
+    halo, recv_op, reqs_in = None, None, []
     if prev is not None:
         halo_p1 = min(plan.padded, (lo + span - 1) * step)
         if halo_p1 > begin:
             halo = ops.empty(ops.rows, halo_p1 - begin)
-            req_in = dist.irecv(halo, src=_peer(group, prev), group=group)
+            recv_op = dist.P2POp(dist.irecv, halo, _peer(group, prev), group)
 
     def seed():
-        nonlocal req_in
-        if req_in is not None:
+        if reqs_in:
             mark('halo_wait_begin')
-            req_in.wait()
+            for q in reqs_in:
+                q.wait()
+            reqs_in.clear()
             ops.seed_partial(begin, halo)
             mark('halo_wait_end')
-            req_in = None
 
     n_tail, y_tail, req_out, sent = 0, None, None, None
     if nxt is not None:
@@ -123,9 +123,21 @@ def run_sharded_track(plan, world, rank, ops, engine_batch, group=None, stats=No
         p1 = min(plan.padded, r1 * step)
         if p1 > end:
             sent = ops.read_partial(end, p1)
-            req_out = dist.isend(sent, dst=_peer(group, nxt), group=group)
             if stats is not None:
                 stats['halo_bytes'] = sent.numel() * sent.element_size()
+    # ONE grouped exchange per rank (ncclGroupStart/End): receive the previous rank's halo, send ours to the next.  Every
+    # rank reaches this point after its first (tail) batch, so nothing waits on a neighbour's remaining model passes.
+    p2p = ([recv_op] if recv_op is not None else []) + \
+          ([dist.P2POp(dist.isend, sent, _peer(group, nxt), group)] if sent is not None else [])
+    if p2p:
+        reqs = dist.batch_isend_irecv(p2p)
+        if recv_op is not None and sent is not None and len(reqs) == 2:
+            reqs_in, req_out = [reqs[0]], reqs[1]
+        elif recv_op is not None:
+            reqs_in = list(reqs)              # backends that coalesce a group hand back one request for all of it
+            req_out = reqs[-1] if sent is not None else None
+        else:
+            req_out = reqs[-1]
     k = lo
     while k < hi - n_tail:
         nb = min(engine_batch, hi - n_tail - k)

@@ -73,6 +73,58 @@ def _ensemble_device(stems, method, weights):
     return out
 
 
+def ensemble_separate(members, mix, device, stem='vocals', method='avg_wave', weights=None, to_host=True, engine_batch=None):
+    """The in-memory form of the GUI's ensemble flow (processing.py:798-1188 runs inference.py once per model, then
+    ensemble.py:258-407 averages the files): every member ``(config, model)`` separates ``mix`` on ``device``, its ``stem``
+    estimate STAYS on the device, and one sesa_ensemble_wave launch reduces them (ensemble.py:172-183).  One upload of the
+    mix, one download of the ensembled stem; no intermediate files, so no intermediate PCM quantisation either (equal to
+    the reference flow with 'wav FLOAT' exports).  Returns ndarray / CUDA tensor [channels, samples]."""
+    from .demix import DemixEngine
+    dev = torch.device(device)
+    if isinstance(mix, torch.Tensor) and mix.device.type == 'cuda':
+        mix_d = mix.to(device=dev, dtype=torch.float32)
+    else:
+        mix_d = torch.as_tensor(np.asarray(mix), dtype=torch.float32).to(dev)
+    stems = []
+    for config, model in members:
+        eng = DemixEngine(config, model, dev, engine_batch=engine_batch)
+        if stem not in eng.instruments:
+            raise KeyError(f'{type(model).__name__} does not produce {stem!r} (it has {eng.instruments})')
+        est = eng.run(mix_d, to_host=False)
+        stems.append(est[eng.instruments.index(stem)])
+    out = ensemble_waveforms(stems, method, weights)
+    if not to_host:
+        return out
+    host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+    host.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return host.numpy()
+
+
+def ensemble_tracks(members, tracks, device, out_dir=None, stem='vocals', method='avg_wave', weights=None, rank=0, world=1,
+                    sample_rate=44100):
+    """BASELINE config 5: many tracks x several models.  Tracks are sharded over the ranks round-robin (independent work:
+    no collective); ``tracks`` is a list of (name, mix) pairs or audio paths.  Every ensembled stem is written as PCM_24
+    like ensemble.py:311 when ``out_dir`` is given.  Returns {name: ndarray} for this rank's tracks."""
+    import os
+    done = {}
+    for i, item in enumerate(tracks):
+        if i % world != rank:
+            continue
+        if isinstance(item, str):
+            name = os.path.splitext(os.path.basename(item))[0]
+            mix, _ = load_audio(item, sample_rate)
+            mix = np.atleast_2d(mix)
+        else:
+            name, mix = item
+        est = ensemble_separate(members, mix, device, stem=stem, method=method, weights=weights)
+        if out_dir is not None:
+            os.makedirs(out_dir, exist_ok=True)
+            write_audio(os.path.join(out_dir, f'{name}_{stem}_ensemble.wav'), est.T, sample_rate, subtype='PCM_24')
+        done[name] = est
+    return done
+
+
 def run_ensemble(files, method, output_path, weights=None, buffer_size=32768):
     """ensemble.py:258-407 reduced to its arithmetic: common sample rate of the first file, common (minimum) length,
     PCM_24 output (:311).  ``buffer_size`` is accepted for argv compatibility (the whole file fits in memory)."""

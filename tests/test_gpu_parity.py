@@ -508,3 +508,43 @@ def test_full_config_c1_mdx23c_30s_demix_vs_oracle():
         ref = odemix.demix(mix, lambda a: omdx.mdx23c_forward(sd_gpu, ocfg, a.cuda()).cpu(), L, ov, bs, 2)
     names = list(sesa.prefer_target_instrument(cfg))
     _check_stems('C1 full config (27 chunks)', names, ref, dict(zip(names, est)))
+
+
+def test_in_memory_ensemble_of_three_models_matches_reference_arithmetic(tmp_path):
+    """BASELINE C5 flow at a small size: BS-RoFormer + Mel-Band-RoFormer + MDX23C separate the same mix, the three vocals
+    estimates are reduced on the device (sesa_ensemble_wave).  Reference arithmetic (ensemble.py:172-183 on the float64
+    buffers soundfile hands it): np.mean / np.average / np.median over the model axis — here applied to each member's own
+    demix() result, which the parity tests above pin to the reference."""
+    import sesa_audio_separation_b200 as sesa
+    from sesa_audio_separation_b200.audio_io import load_audio
+    from sesa_audio_separation_b200.ensemble import ensemble_separate, ensemble_tracks
+    L = 441 * 32
+    members, singles = [], []
+    mix = synth_mix(L * 2 + 700, 2, seed=77)
+    for name in ('bs_small', 'mel_small', 'mdx_small'):
+        case = CASES[name]
+        model, _ = build(case)
+        if name == 'mdx_small':
+            Lm = case['cfg']['audio']['chunk_size']
+            cfg = sesa.ConfigDict(dict(audio=case['cfg']['audio'], inference=dict(num_overlap=2, batch_size=1),
+                                       training=case['cfg']['training']))
+        else:
+            cfg = sesa.ConfigDict(dict(audio=dict(chunk_size=L), inference=dict(num_overlap=2, batch_size=1),
+                                       training=dict(instruments=['vocals', 'other'], target_instrument=None if name == 'mel_small' else 'vocals')))
+        members.append((cfg, model))
+        singles.append(sesa.demix(cfg, model, mix, 'cuda', case['kind'])['vocals'])
+    f64 = np.stack([s.astype(np.float64) for s in singles], 0)
+    got = ensemble_separate(members, mix, 'cuda', stem='vocals')
+    assert np.array_equal(got, np.mean(f64, axis=0).astype(np.float32))
+    w = np.array([2.0, 1.0, 1.0], dtype=np.float32)
+    w /= w.sum()
+    got_w = ensemble_separate(members, mix, 'cuda', stem='vocals', weights=[2.0, 1.0, 1.0])
+    assert np.array_equal(got_w, np.average(f64, axis=0, weights=w).astype(np.float32))
+    assert np.array_equal(ensemble_separate(members, mix, 'cuda', stem='vocals', method='median_wave'),
+                          np.median(f64, axis=0).astype(np.float32))
+    # track sharding (rank r of W takes tracks r, r+W, ...) and the PCM_24 output of ensemble.py:311
+    tracks = [(f't{i}', mix * (1.0 - 0.1 * i)) for i in range(3)]
+    done = ensemble_tracks(members, tracks, 'cuda', out_dir=str(tmp_path), rank=1, world=2)
+    assert list(done) == ['t1']
+    back, _ = load_audio(str(tmp_path / 't1_vocals_ensemble.wav'), 44100)
+    assert np.abs(back - done['t1']).max() <= 2.0 ** -23 + 1e-9
