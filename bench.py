@@ -477,6 +477,13 @@ def main():
                 line['kernels'][k].update({'isolated_us_per_launch': round(v['us'], 1), 'isolated_achieved': v['gbs'],
                                            'isolated_frac': v['gbs'] / hbm_peak})
             torch.cuda.empty_cache()
+            # and at a launch size that saturates the memory system (16 chunks per launch = 4x the product's engine batch):
+            # separates what the KERNEL reaches from what a 10-70 us launch can reach at all
+            big = hbm_bench.measure(chunks=16, reps=5, seconds=args.seconds)
+            for k, v in big.items():
+                line['kernels'][k].update({'saturated_us_per_launch': round(v['us'], 1), 'saturated_achieved': v['gbs'],
+                                           'saturated_frac': v['gbs'] / hbm_peak, 'saturated_chunks_per_launch': 16})
+            torch.cuda.empty_cache()
         if world == 1 and tc_mode and args.precision == 'fp32' and not args.no_configs:
             line['configs'] = {name: sub_config(name, dev, tf_peak, hbm_peak) for name in ('c1_mdx23c', 'c3_mel4')}
         if world == 1 and not args.no_cpu_baseline:

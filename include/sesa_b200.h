@@ -48,7 +48,9 @@ typedef struct sesa_gemm_epilogue {
   int32_t rot_cols; /* rotary embedding on column pairs n < rot_cols (bs_roformer.py:112-113) */
   int32_t rot_dim;  /* head dim */
   int32_t pos_div, pos_mod; /* sequence position of row m = (m / pos_div) % pos_mod */
-  const float* rot; /* [pos_mod][rot_dim/2][2] = (cos, sin) */
+  const float* rot; /* sesa_gemm_simt: [pos_mod][rot_dim/2][2] = (cos, sin) per position and column pair;
+                       sesa_gemm_tc: the same values quad-major, [rot_dim/4][pos_mod][4] = (cos, sin, cos, sin) of the two
+                       pairs of a column quad, so that rows at consecutive positions read consecutive 16-byte words */
 } sesa_gemm_epilogue;
 
 int sesa_abi_version(void);

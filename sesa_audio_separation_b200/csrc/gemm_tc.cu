@@ -373,8 +373,11 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
           const float4 s4 = __ldg(reinterpret_cast<const float4*>(g->rowss) + rowc);
           rs = 1.0f / fmaxf(sqrtf(((s4.x + s4.y) + s4.z) + s4.w), 1e-12f);
         }
-        int64_t rot_row = 0;   // float4 index of this row's (cos, sin) pairs in the rotary table
-        if (FLAVOR == F_ROT && rot_cols > 0) rot_row = (int64_t)((row / ep.pos_div) % ep.pos_mod) * (ep.rot_dim >> 2);
+        // rotary table, quad-major: float4 (cos, sin, cos, sin) of column-pair quad qd at position pos sits at index
+        // qd * pos_mod + pos, so the 32 rows of a warp (consecutive positions on the band axis, one or two positions on
+        // the time axis) read consecutive or identical 16-byte words: 4 cache lines per warp load instead of 32
+        int64_t rot_row = 0;   // this row's position
+        if (FLAVOR == F_ROT && rot_cols > 0) rot_row = (int64_t)((row / ep.pos_div) % ep.pos_mod);
         {   // bias slice of the warp's columns -> shared memory (lane -> 4 consecutive columns)
           float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias != nullptr && lane * 4 < HALF) bq = __ldg(reinterpret_cast<const float4*>(bias + n_half) + lane);   // interior tile: in range
@@ -393,9 +396,9 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
         auto load_cs = [&](int cstep) {
           const int nn = n_half + cstep * EPI_COLS;
           if (FLAVOR == F_ROT && cstep < HALF / EPI_COLS && nn < rot_cols) {
-            const float4* rp = reinterpret_cast<const float4*>(ep.rot) + rot_row + ((nn % ep.rot_dim) >> 2);
+            const float4* rp = reinterpret_cast<const float4*>(ep.rot) + (int64_t)((nn % ep.rot_dim) >> 2) * ep.pos_mod + rot_row;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) cs[k] = __ldg(rp + k);
+            for (int k = 0; k < 4; ++k) cs[k] = __ldg(rp + (int64_t)k * ep.pos_mod);
           }
         };
         load_cs(0);
@@ -557,7 +560,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
           const int rd = ((nn + c4 * 4) % ep.rot_dim) >> 1;
 #pragma unroll
           for (int it = 0; it < 4; ++it)
-            cs4[it] = __ldg(reinterpret_cast<const float4*>(ep.rot) + (((int64_t)pos4[it] * (ep.rot_dim >> 1) + rd) >> 1));
+            cs4[it] = __ldg(reinterpret_cast<const float4*>(ep.rot) + ((int64_t)(rd >> 1) * ep.pos_mod + pos4[it]));
         }
       };
       load_rot(0);

@@ -253,10 +253,13 @@ class _RoformerBase(KernelModule):
     def _rot_table(self, prep, freqs, n):
         """(cos, sin) of pos*freq for pos < n — computed exactly like the reference's rotary module
         (fp32 outer product, then cos/sin), oracle/third_party.py."""
-        key = (tuple(freqs.tolist()), n)
+        key = (tuple(freqs.tolist()), n, self._tc)
         if key not in prep['rot']:
             ang = torch.einsum('i,j->ij', torch.arange(n, dtype=torch.float32), freqs)
-            prep['rot'][key] = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous().to(self._device)
+            tab = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()           # [pos][dh/2][2]
+            if self._tc:    # quad-major for the tensor-core epilogue: [dh/4][pos][4] (include/sesa_b200.h)
+                tab = tab.reshape(n, -1, 4).permute(1, 0, 2).contiguous()
+            prep['rot'][key] = tab.to(self._device)
         return prep['rot'][key]
 
     # ------------------------------------------------------------------ workspace per batch size

@@ -294,7 +294,7 @@ def _tc_case(lib, M, N, K, nsplit, block_n, bias=True, act=0, rowscale=False, re
         ang = torch.einsum('i,j->ij', torch.arange(pos_mod, dtype=torch.float32),
                            1.0 / (10000 ** (torch.arange(0, rot_dim, 2).float() / rot_dim)))
         rot_t = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
-        rot_d = rot_t.to(dev)
+        rot_d = rot_t.reshape(pos_mod, -1, 4).permute(1, 0, 2).contiguous().to(dev)    # quad-major layout of sesa_gemm_tc
         ep = GemmEpilogue(0, act, 1 if residual else 0, 0, rot_cols, rot_dim, pos_div, pos_mod, rot_d.data_ptr())
     tab.run(ep, nsplit=nsplit, out_planes=2)
     torch.cuda.synchronize()
@@ -352,6 +352,7 @@ def test_gemm_tc_ragged_and_epilogues(lib, cg):
     assert _tc_case(lib, 640, 2048, 512, 3, 256, act=1, rowscale=True, planes_out=True, seed=5, cg=cg) < 3e-5
     assert _tc_case(lib, 640, 512, 2048, 3, 256, residual=True, planes_out=True, seed=6, cg=cg) < 3e-5
     assert _tc_case(lib, 62 * 9, 1536, 512, 3, 256, bias=False, rot=(1024, 64, 62, 9), planes_out=True, seed=7, cg=cg) < 3e-5
+    assert _tc_case(lib, 62 * 9, 1536, 512, 3, 256, bias=False, rot=(1024, 64, 1, 62), planes_out=True, seed=8, cg=cg) < 3e-5
     assert _tc_case(lib, 200, 24, 8, 3, 256, seed=8, cg=cg) < 3e-5
 
 

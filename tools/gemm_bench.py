@@ -42,7 +42,8 @@ def main():
     b1 = torch.randn(2048, device=dev, generator=g)
     b2 = torch.randn(512, device=dev, generator=g)
     ang = torch.einsum('i,j->ij', torch.arange(801, dtype=torch.float32), 1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64)))
-    rot = torch.stack([ang.cos(), ang.sin()], -1).contiguous().to(dev)
+    rot = torch.stack([ang.cos(), ang.sin()], -1).reshape(801, -1, 4).permute(1, 0, 2).contiguous().to(dev)   # quad-major
+    rot_band = torch.stack([ang[:62].cos(), ang[:62].sin()], -1).reshape(62, -1, 4).permute(1, 0, 2).contiguous().to(dev)
 
     def table(A, W, N, K, **kw):
         return tc.TcGemmTable([dict(A=tc.planes_arg(A), W=tc.planes_arg(W), M=M, N=N, K=K, **kw)], dev, block_n=args.block_n, cta_group=args.cta_group)
@@ -57,6 +58,9 @@ def main():
         'qkvg': (table(xp, w['qkvg'], 1544, 512, C=(gates.data_ptr(), 8), P=tc.planes_arg(qkvp), bias=bg.data_ptr(),
                        rowss=ss.data_ptr(), ss_slots=4, p_cols=1536, c_col0=1536),
                  GemmEpilogue(0, 0, 0, 0, 1024, 64, 62, 801, rot.data_ptr()), 2 * M * 1544 * 512),
+        'qkvg_band': (table(xp, w['qkvg'], 1544, 512, C=(gates.data_ptr(), 8), P=tc.planes_arg(qkvp), bias=bg.data_ptr(),
+                            rowss=ss.data_ptr(), ss_slots=4, p_cols=1536, c_col0=1536),
+                      GemmEpilogue(0, 0, 0, 0, 1024, 64, 1, 62, rot_band.data_ptr()), 2 * M * 1544 * 512),
         'qkvp': (table(xp, w['qkv'], 1536, 512, P=tc.planes_arg(qkvp), rowss=ss.data_ptr(), ss_slots=4),
                  GemmEpilogue(0, 0, 0, 0, 1024, 64, 62, 801, rot.data_ptr()), 2 * M * 1536 * 512),
         'outp': (table(xp, w['out'], 512, 512, C=(x.data_ptr(), 512), P=tc.planes_arg(xp2), ss_out=ss.data_ptr()),
@@ -77,7 +81,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.reps
-        print(f'{name:6s} M={M} nsplit={args.nsplit} BN={args.block_n} CG={args.cta_group}: {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s algorithmic '
+        print(f'{name:9s} M={M} nsplit={args.nsplit} BN={args.block_n} CG={args.cta_group}: {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s algorithmic '
               f'({flops * (3 if args.nsplit == 3 else 1) / ms / 1e9:8.1f} MMA TFLOP/s)')
 
 
