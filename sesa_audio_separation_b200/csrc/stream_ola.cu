@@ -65,12 +65,23 @@ __global__ void __launch_bounds__(256) overlap_accumulate_kernel(const AccArgs a
       if (o64 >= 0 && o64 < n) {
         const int o = (int)o64;
         oq[j] = o;
+        if (V == 4 && o + 3 < n) {     // whole quad inside the chunk: one 128-bit window load (o, L and fade positions: o % 4 == 0)
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.window + o));
+          float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          if (o + e < n) {
-            const float w = fade_window(a.window, o + e, a.L, a.fade, kind);
-            wq[j][e] = w;
-            cnt[e] = __fadd_rn(cnt[e], w);
+          for (int e = 0; e < V; ++e) {
+            if ((kind == 1 && o + e < a.fade) || (kind == 2 && o + e >= a.L - a.fade)) w[e] = 1.0f;
+            wq[j][e] = w[e];
+            cnt[e] = __fadd_rn(cnt[e], w[e]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            if (o + e < n) {
+              const float w = fade_window(a.window, o + e, a.L, a.fade, kind);
+              wq[j][e] = w;
+              cnt[e] = __fadd_rn(cnt[e], w);
+            }
           }
         }
       }
@@ -171,7 +182,8 @@ extern "C" int sesa_overlap_accumulate(const float* y, int k0, int nb, const int
   a.L = (int)chunk_size; a.fade = fade; a.nc = nstems * channels; a.span = (int)span; a.r_begin = r_begin;
   const bool vec = (step & 3) == 0 && (chunk_size & 3) == 0 && (crop & 3) == 0 && (part_ld & 3) == 0 && (part_p0 & 3) == 0 &&
                    (out_ld & 3) == 0 && (out_q0 & 3) == 0 && span <= 8 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(partial) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+                   (reinterpret_cast<uintptr_t>(partial) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(window) & 15) == 0;
   const int regions = r_end - r_begin;
   cudaStream_t st = (cudaStream_t)stream;
   if (vec) {
