@@ -227,6 +227,13 @@ int sesa_overlap_add_range(const float* chunk_out, const int64_t* starts, const 
                            const float* init, int64_t init_p0, int64_t init_len, int mode, int64_t crop,
                            int64_t out_len, float* out, void* stream);
 
+/* RMSNorm at the end of a Mel-Band Transformer (mel_band_roformer.py:218,226) fused with the operand preparation of the
+ * next GEMM: x[rows][dim] <- x / max(||x||, 1e-12) * sqrt(dim) * gamma in place, planes <- bf16 hi/lo of the new rows,
+ * ss_out[row][ss_slots] <- (sum of squares of the new row, 0, ...).  Bit-identical to sesa_rmsnorm followed by
+ * sesa_prep_rows(normalize = 2). */
+int sesa_rmsnorm_planes(float* x, const float* gamma, int64_t rows, int dim, void* planes, int64_t ldp, int64_t p_plane,
+                        int out_planes, float* ss_out, int ss_slots, void* stream);
+
 /* ---- streaming overlap-add (the product path of utils.py:439-464) ---------------------------- */
 /* Folds the model outputs y[nb][n][c][L] of chunks [k0, k0+nb) into the track result, one call per engine batch, in
  * ascending chunk order per sample (result += x * window).  The padded mix is cut into step-long regions; regions

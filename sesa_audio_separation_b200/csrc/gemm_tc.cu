@@ -1078,6 +1078,58 @@ extern "C" int sesa_prep_rows(const float* x, int64_t ldx, int64_t rows, int dim
   return SESA_OK;
 }
 
+// Mel-Band-RoFormer ends every Transformer with an RMSNorm (mel_band_roformer.py:218,226) whose output IS the new residual
+// stream.  One warp per row: y = x / max(||x||, 1e-12) * sqrt(dim) * gamma written back in place (the arithmetic and order of
+// rmsnorm_kernel, misc.cu), then — from the row the warp has just written — the bf16 hi/lo planes of y and its sum of
+// squares (slot 0) for the fused RMSNorm of the consuming GEMM (the arithmetic and order of prep_rows_kernel, normalize 2).
+// One read of x and one launch instead of two reads and two launches; bit-identical to the two-kernel sequence.
+__global__ void __launch_bounds__(256) rmsnorm_planes_kernel(float* __restrict__ x, const float* __restrict__ gamma, int64_t rows,
+                                                             int dim, float scale, __nv_bfloat16* __restrict__ planes, int64_t ldp,
+                                                             int64_t p_plane, int out_planes, float* __restrict__ ss_out,
+                                                             int ss_slots) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* xr = x + row * dim;
+  float ss = 0.f;
+  for (int i = lane; i < dim; i += 32) ss += xr[i] * xr[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int i = lane; i < dim; i += 32) xr[i] = xr[i] * inv * scale * gamma[i];
+  __syncwarp();
+  const int nv = dim >> 2;
+  float s2 = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + 4 * i);
+    s2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  if (ss_out != nullptr && lane < ss_slots) ss_out[row * ss_slots + lane] = lane == 0 ? s2 : 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + 4 * i);
+    __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+    tc::split_bf16(v.x, h0, l0); tc::split_bf16(v.y, h1, l1);
+    tc::split_bf16(v.z, h2, l2); tc::split_bf16(v.w, h3, l3);
+    __nv_bfloat16* pr = planes + row * ldp + 4 * i;
+    *reinterpret_cast<uint2*>(pr) = make_uint2(tc::pack_bf16(h0, h1), tc::pack_bf16(h2, h3));
+    if (out_planes > 1) *reinterpret_cast<uint2*>(pr + p_plane) = make_uint2(tc::pack_bf16(l0, l1), tc::pack_bf16(l2, l3));
+  }
+}
+
+extern "C" int sesa_rmsnorm_planes(float* x, const float* gamma, int64_t rows, int dim, void* planes, int64_t ldp, int64_t p_plane,
+                                   int out_planes, float* ss_out, int ss_slots, void* stream) {
+  SESA_CHECK_ARG(dim > 0 && (dim & 3) == 0, "sesa_rmsnorm_planes: dim must be a multiple of 4");
+  SESA_CHECK_ARG(planes != nullptr && (ldp & 3) == 0 && (p_plane & 3) == 0, "sesa_rmsnorm_planes: planes with strides that are multiples of 4");
+  SESA_CHECK_ARG((out_planes == 1 || out_planes == 2) && ss_slots >= 1 && ss_slots <= 32, "sesa_rmsnorm_planes: bad out_planes / ss_slots");
+  if (rows <= 0) return SESA_OK;
+  rmsnorm_planes_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, gamma, rows, dim, sqrtf((float)dim), reinterpret_cast<__nv_bfloat16*>(planes), ldp, p_plane, out_planes, ss_out, ss_slots);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
 // BandSplit prologue (bs_roformer.py:241-249; Mel :250-258): per (row, band) L2-normalise the band's slice of the feature
 // row (F.normalize of RMSNorm; gamma*sqrt(dim_in) is folded into the band's weight) and write it as bf16 hi/lo planes at
 // the band's 16-byte aligned plane column — the A operand of the grouped tensor-core GEMM.  One warp per (row, band).

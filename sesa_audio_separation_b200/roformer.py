@@ -481,9 +481,12 @@ class _RoformerBase(KernelModule):
             self._gemm(g['ff1'], _epilogue(rownorm=1, act=_lib.ACT_GELU))
             self._gemm(g['ff2'], _epilogue(residual=1))
         if tr['norm'] is not None:
-            call('sesa_rmsnorm', _ptr(ws['x']), _ptr(tr['norm']), _ptr(ws['x']), M, D, _stream())
-            if self._tc:
-                self._refresh_planes(ws)
+            if self._tc:    # output RMSNorm + planes / row sums of squares of the new residual stream in one pass
+                xp = ws['xp']
+                call('sesa_rmsnorm_planes', _ptr(ws['x']), _ptr(tr['norm']), M, D, _ptr(xp), xp.shape[-1], xp.stride(0),
+                     2 if self.precision == 'fp32' else 1, _ptr(ws['ss']), ws['ss_slots'], _stream())
+            else:
+                call('sesa_rmsnorm', _ptr(ws['x']), _ptr(tr['norm']), _ptr(ws['x']), M, D, _stream())
 
     def forward(self, raw_audio, target=None, return_loss_breakdown=False, out=None):
         if target is not None:

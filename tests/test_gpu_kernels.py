@@ -734,3 +734,29 @@ def test_ensemble_wave_kernel_matches_numpy_on_float64(lib):
                               np.median(f64[:n], axis=0).astype(np.float32))
         assert np.array_equal(sesa.ensemble_waveforms(dev_stems[:n], 'max_wave').cpu().numpy(), np.max(f64[:n], axis=0).astype(np.float32))
         assert np.array_equal(sesa.ensemble_waveforms(dev_stems[:n], 'min_wave').cpu().numpy(), np.min(f64[:n], axis=0).astype(np.float32))
+
+
+@pytest.mark.parametrize('dim,out_planes', [(384, 2), (512, 2), (64, 1)])
+def test_rmsnorm_planes_equals_the_two_kernel_sequence(lib, dim, out_planes):
+    """sesa_rmsnorm_planes (Mel per-transformer output norm + operand preparation in one pass) is bit-identical to
+    sesa_rmsnorm followed by sesa_prep_rows(normalize=2), and matches the torch statement of RMSNorm."""
+    from sesa_audio_separation_b200 import tc
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(dim)
+    rows, slots = 1237, 4
+    x = torch.randn(rows, dim, device=dev, generator=g) * 3
+    gamma = 1 + 0.1 * torch.randn(dim, device=dev, generator=g)
+    a = x.clone()
+    pa = tc.alloc_planes(rows, dim, dev)
+    sa = torch.full((rows, slots), 7.0, device=dev)
+    lib.call('sesa_rmsnorm', P(a), P(gamma), P(a), rows, dim, S())
+    tc.prep_rows(a, rows, dim, dim, pa, 2, rowinv=sa, ss_slots=slots, out_planes=out_planes)
+    b = x.clone()
+    pb = tc.alloc_planes(rows, dim, dev)
+    sb = torch.full((rows, slots), 9.0, device=dev)
+    lib.call('sesa_rmsnorm_planes', P(b), P(gamma), rows, dim, P(pb), pb.shape[-1], pb.stride(0), out_planes, P(sb), slots, S())
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(sa, sb)
+    assert torch.equal(pa[:out_planes], pb[:out_planes])
+    ref = torch.nn.functional.normalize(x, dim=-1) * dim ** 0.5 * gamma
+    assert max_rel(ref.cpu().numpy(), b.cpu().numpy()) < 1e-6
