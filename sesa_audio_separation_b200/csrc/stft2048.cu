@@ -318,8 +318,24 @@ __global__ void __launch_bounds__(FT, 3) mask_istft2048_kernel(
   auto z_lo = [](float2 yl, float2 yr) { return make_float2(yl.x - yr.y, yl.y + yr.x); };
   auto z_hi = [](float2 yl, float2 yr) { return make_float2(yl.x + yr.y, yr.x - yl.y); };
 
+  // 128-byte lines of one frame's spectrum row and mask row (for the L2 prefetch of the next frame below)
+  const int spec_lines = (F * C * 8 + 127) / 128;
+  const int mask_lines = MODE == 0 ? spec_lines : MODE == 1 ? (J * 8 + 127) / 128 : 0;
   for (int t = t_lo; t <= t_hi; ++t) {
     const int64_t row = (int64_t)b * T + t;
+    if (t < t_hi) {
+      // the NEXT frame's rows are requested into L2 now (no registers held), so that its 16 loads per thread, issued
+      // right after this frame's transform, pay the L2 latency instead of the HBM latency: the CTA has only four warps
+      // and nothing else to run while a frame's operands are in flight
+      const char* sp_next = reinterpret_cast<const char*>(
+          spec + (MODE == 2 ? (((int64_t)b * nstems + n) * T + (t + 1)) : (row + 1)) * (int64_t)F * C * 2);
+      for (int l = tid; l < spec_lines; l += FT) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp_next + (int64_t)l * 128));
+      if (MODE != 2) {
+        const char* mk_next = reinterpret_cast<const char*>(
+            mask + ((int64_t)n * nb * T + row + 1) * (MODE == 0 ? (int64_t)F * C * 2 : (int64_t)J * 2));
+        for (int l = tid; l < mask_lines; l += FT) asm volatile("prefetch.global.L2 [%0];" ::"l"(mk_next + (int64_t)l * 128));
+      }
+    }
     // a[k] = Z[qa + 256 k], b[k] = Z[qb + 256 k], k = 0..7, built from bins f <= 1024 only
     float2 a[8], bb[8];
     if (tid != 0) {

@@ -548,3 +548,91 @@ def test_in_memory_ensemble_of_three_models_matches_reference_arithmetic(tmp_pat
     assert list(done) == ['t1']
     back, _ = load_audio(str(tmp_path / 't1_vocals_ensemble.wav'), 44100)
     assert np.abs(back - done['t1']).max() <= 2.0 ** -23 + 1e-9
+
+
+class _FakeDist:
+    """In-process stand-in for the torch.distributed point-to-point calls distributed.py uses: two 'ranks' run as two
+    threads on the same GPU and exchange tensors through queues (NCCL refuses two ranks on one device; the real NCCL path is
+    exercised by bench.py's `strong` record and tools/shard_check.py on 2-8 GPUs, the choreography by the gloo tests)."""
+
+    def __init__(self, world):
+        import queue
+        import threading
+        self.q = {(s, d): queue.Queue() for s in range(world) for d in range(world)}
+        self.local = threading.local()
+
+    class P2POp:
+        def __init__(self, op, tensor, peer, group=None):
+            self.op, self.tensor, self.peer = op, tensor, peer
+
+    class _Req:
+        def __init__(self, fn):
+            self.fn, self.done = fn, False
+
+        def wait(self):
+            if not self.done:
+                self.fn()
+                self.done = True
+
+    def isend(self, tensor, dst, group=None):
+        torch.cuda.synchronize()
+        self.q[(self.local.rank, dst)].put(tensor.detach().clone())
+        return self._Req(lambda: None)
+
+    def irecv(self, tensor, src, group=None):
+        rank = self.local.rank
+
+        def finish():
+            tensor.copy_(self.q[(src, rank)].get(timeout=120))
+            torch.cuda.synchronize()
+        return self._Req(finish)
+
+    def batch_isend_irecv(self, ops):
+        sends = [self.isend(o.tensor, o.peer) for o in ops if o.op == self.isend]
+        recvs = [self.irecv(o.tensor, o.peer) for o in ops if o.op == self.irecv]
+        return recvs + sends if recvs else sends
+
+    def get_global_rank(self, group, r):
+        return r
+
+
+@pytest.mark.parametrize('name,world,ov', [('bs_small', 2, 4), ('mel_small', 3, 2)])
+def test_chunk_range_sharding_on_the_gpu_path_is_bit_identical(monkeypatch, name, world, ov):
+    """DemixEngine(world, rank) through the real CUDA path (slice upload + sesa_pad_reflect_slice, tail-first order,
+    sesa_overlap_accumulate continuing from the received halo, grouped gather) with `world` ranks as threads on one GPU:
+    the root's result equals the unsharded run bit for bit, and every rank uploads only its slice of the mix."""
+    import threading
+    import sesa_audio_separation_b200 as sesa
+    from sesa_audio_separation_b200 import distributed
+    case = CASES[name]
+    L = 441 * 32
+    cfg = sesa.ConfigDict(dict(audio=dict(chunk_size=L), inference=dict(num_overlap=ov, batch_size=1),
+                               training=dict(instruments=['vocals', 'other'],
+                                             target_instrument=None if name == 'mel_small' else 'vocals')))
+    mix = synth_mix(L * 6 + 1234, 2, seed=71)
+    ref_model, _ = build(case)
+    ref = sesa.DemixEngine(cfg, ref_model, 'cuda', engine_batch=3).run(mix)
+    fake = _FakeDist(world)
+    monkeypatch.setattr(distributed, 'dist', fake)
+    out, err, stats = {}, [], {}
+
+    def worker(rank):
+        try:
+            fake.local.rank = rank
+            model, _ = build(case)
+            eng = sesa.DemixEngine(cfg, model, 'cuda', engine_batch=3, world=world, rank=rank)
+            out[rank] = eng.run(mix)
+            stats[rank] = dict(eng.stats)
+        except Exception as e:          # surface failures of either thread in the main thread
+            import traceback
+            err.append((rank, traceback.format_exc()))
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not err, err
+    assert all(out[r] is None for r in range(1, world))
+    assert out[0].shape == ref.shape
+    assert np.array_equal(out[0], ref)
+    assert all(0 < stats[r]['h2d_bytes'] < mix.nbytes for r in range(world)), stats
