@@ -346,9 +346,10 @@ def main():
                 'value': cb['value'], 'unit': 'x realtime', 'n_gpus': args.gpus, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': cb['s_per_chunk'] * 1e3, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': dict(base_cfg, note='reference CPU path: the oracle port of utils.demix + BSRoformer.forward with the '
-                               "reference's stock CPU attention (SDPA); the reference package itself cannot be installed/imported "
-                               'on the GPU box (script collection, absent third-party deps); a step = one chunk of the 96-chunk loop'),
+                'config': dict(base_cfg),      # the same keys and values as the b200 arm's `config`
+                'note': 'reference CPU path: the oracle port of utils.demix + BSRoformer.forward with the '
+                        "reference's stock CPU attention (SDPA); the reference package itself cannot be installed/imported "
+                        'on the GPU box (script collection, absent third-party deps); a step = one chunk of the 96-chunk loop',
                 'cpu_baseline': {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                 'e2e': {'value': cb['value'], 'unit': 'x realtime', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
@@ -448,7 +449,8 @@ def main():
             'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'bf16x3 (split-bf16 tensor-core products, fp32 accumulate: fp32-parity mode)',
                       'bf16': 'bf16 (fp32 accumulate)', 'fp32_simt': 'f32'}[args.precision], 'data': 'synthetic',
-            'config': dict(base_cfg, engine_batch=args.engine_batch, precision=args.precision),
+            'config': dict(base_cfg),
+            'engine': {'engine_batch': args.engine_batch, 'precision': args.precision},
             'e2e': {'value': audio_s / float(t_e2e.item()), 'unit': 'x realtime',
                     'h2d_bytes_per_step': int(mix_host.numel() * 4), 'd2h_bytes_per_step': int(out_bytes)},
             'gpu_launches': int(launches), 'clocks': clocks,
