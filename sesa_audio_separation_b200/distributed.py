@@ -31,17 +31,24 @@ import torch.distributed as dist
 from .plan import shard_chunks
 
 
-def shard_layout(plan, world):
-    """[(lo, hi, own_begin, own_end)] per rank in padded coordinates; inactive ranks get lo == hi."""
+def shard_layout(plan, world, strict=False):
+    """[(lo, hi, own_begin, own_end)] per rank in padded coordinates; inactive ranks get lo == hi.
+
+    Every rank but the last must hold at least ``span - 1`` chunks (what the next rank's first regions depend on).  A track
+    too short for ``world`` ranks is sharded over the largest number of ranks that satisfies this and the remaining ranks
+    stay idle (every rank derives the same layout from the schedule alone); ``strict=True`` raises instead."""
     n, L = plan.n_chunks, plan.chunk_size
-    ranges = [shard_chunks(n, world, r) for r in range(world)]
-    active = [r for r in range(world) if ranges[r][1] > ranges[r][0]]
     ov_reach = -(-L // plan.step) - 1            # chunks of the previous range that reach into ours
-    for r in active[:-1]:
-        lo, hi = ranges[r]
-        if hi - lo < ov_reach:
+    for w in range(world, 0, -1):
+        ranges = [shard_chunks(n, w, r) if r < w else (n, n) for r in range(world)]
+        active = [r for r in range(world) if ranges[r][1] > ranges[r][0]]
+        short = [r for r in active[:-1] if ranges[r][1] - ranges[r][0] < ov_reach]
+        if not short:
+            break
+        if strict:
+            r = short[0]
             raise ValueError(f'chunk-range sharding needs at least {ov_reach} chunks per rank '
-                             f'(rank {r} has {hi - lo}); use fewer ranks for this track')
+                             f'(rank {r} has {ranges[r][1] - ranges[r][0]}); use fewer ranks for this track')
     out = []
     for r in range(world):
         lo, hi = ranges[r]

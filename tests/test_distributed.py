@@ -153,7 +153,7 @@ def _reference(length, L, ov, bs):
     return np.asarray(odemix.demix(mix, model, L, ov, bs, 2)).reshape(4, length)
 
 
-@pytest.mark.parametrize('world,length,L,ov,bs,eb', [(2, 23456, 1000, 4, 2, 4), (3, 30011, 1000, 4, 1, 3), (2, 9000, 1000, 2, 3, 4),
+@pytest.mark.parametrize('world,length,L,ov,bs,eb', [(3, 1000, 1000, 4, 1, 4), (3, 2500, 1000, 4, 1, 4), (2, 23456, 1000, 4, 2, 4), (3, 30011, 1000, 4, 1, 3), (2, 9000, 1000, 2, 3, 4),
                                                       (3, 40000, 1000, 8, 4, 4), (2, 4100, 1000, 1, 1, 2), (3, 26000, 1001, 3, 2, 2)])
 def test_sharded_overlap_add_equals_single_process(tmp_path, world, length, L, ov, bs, eb):
     out_path = str(tmp_path / 'res.npy')
@@ -197,6 +197,12 @@ def test_shard_layout_rejects_too_many_ranks():
     from sesa_audio_separation_b200.plan import make_plan
     plan = make_plan(6000, 1000, 4, 1)
     with pytest.raises(ValueError):
-        shard_layout(plan, 16)
+        shard_layout(plan, 16, strict=True)
     lay = shard_layout(plan, 2)
     assert lay[0][2] == 0 and lay[0][3] == lay[1][2] and lay[1][3] == plan.padded
+    # a track too short for the ranks offered is sharded over fewer of them; the others stay idle
+    lay = shard_layout(plan, 16)
+    active = [r for r in range(16) if lay[r][1] > lay[r][0]]
+    assert active == list(range(len(active))) and 1 <= len(active) < 16
+    assert all(lay[r][1] - lay[r][0] >= 3 for r in active[:-1])
+    assert lay[active[-1]][3] == plan.padded and sum(l[1] - l[0] for l in lay) == plan.n_chunks
