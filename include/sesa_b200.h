@@ -197,6 +197,10 @@ int sesa_norm_act_split(const float* x, int mode, int batch, int64_t n1, int cha
                         int64_t p_plane, void* stream);
 /* x[(bt*F + f)*ld + c] += g[(bt*C + c)*F + f]: "x = x + tdf(x)" (:134) with the TDF output channel-major. */
 int sesa_transpose_add(float* x, const float* g, int64_t bt, int F, int channels, int64_t ld, void* stream);
+/* The same update fused with the InstanceNorm2d statistics of its result (the norm of tfc2, :124,135): stats[b][c] =
+ * (mean, 1/sqrt(var + eps)) of the updated x over (frames, F); scratch: 2*batch*channels doubles. */
+int sesa_transpose_add_stats(float* x, const float* g, int batch, int64_t frames, int F, int channels, int64_t ld,
+                             double* scratch, float* stats, float eps, void* stream);
 /* cac2cws (:191-196): spec (sesa_stft layout 0, [bt][f_full][c2]) -> mix[bt][fs][c2*k + kk], f_full = kk*fs + f'. */
 int sesa_mdx_pack(const float* spec, int64_t bt, int f_full, int fs, int k, int c2, float* mix, void* stream);
 /* planes[r] = split([mix[r] | x[r] * first[r]]): "x * first_conv_out" and cat([mix, x]) (:228-230). */

@@ -79,6 +79,8 @@ _SIGS = {
     'sesa_norm_act_split': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                     c_int, c_void_p, c_int64, c_int64, c_void_p]),
     'sesa_transpose_add': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p]),
+    'sesa_transpose_add_stats': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                         ctypes.c_float, c_void_p]),
     'sesa_mdx_pack': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'sesa_mdx_final_concat': (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_void_p,
                                       c_int64, c_int64, c_void_p]),
@@ -129,7 +131,7 @@ def check(status):
 # ---- launch accounting / per-kernel-class timing (bench.py, profiling); off by default
 LAUNCHES = 0
 _profile = None   # dict: class -> [ (start_event, end_event), ... ] when enabled
-_CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_rmsnorm_planes': 'prep_rows', 'sesa_rmsnorm': 'prep_rows', 'sesa_add_inplace': 'prep_rows', 'sesa_band_prep': 'prep_rows', 'sesa_instnorm_stats': 'norm', 'sesa_norm_act_split': 'norm', 'sesa_transpose_add': 'norm', 'sesa_attention_simt': 'attention',
+_CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_rmsnorm_planes': 'prep_rows', 'sesa_rmsnorm': 'prep_rows', 'sesa_add_inplace': 'prep_rows', 'sesa_band_prep': 'prep_rows', 'sesa_instnorm_stats': 'norm', 'sesa_norm_act_split': 'norm', 'sesa_transpose_add': 'norm', 'sesa_transpose_add_stats': 'norm', 'sesa_attention_simt': 'attention',
           'sesa_attention_tc': 'attention', 'sesa_stft': 'stft', 'sesa_mask_istft': 'mask_istft',
           'sesa_overlap_add': 'overlap_add', 'sesa_overlap_add_range': 'overlap_add', 'sesa_overlap_accumulate': 'overlap_add', 'sesa_pad_reflect_slice': 'framing',
           'sesa_tta_variants': 'tta', 'sesa_tta_combine': 'tta', 'sesa_ensemble_wave': 'ensemble', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}

@@ -354,6 +354,54 @@ __global__ void __launch_bounds__(256) transpose_add_kernel(float* __restrict__ 
   }
 }
 
+// The same update, and the InstanceNorm statistics of its RESULT on the way (the next thing the reference does with
+// x + tdf(x) is tfc2's norm, :135): a block walks `fs` consecutive 32-frequency tiles of one (bt, 32-channel) column, keeps
+// per-thread partial sums of the new values (fp32 over <= 4*fs values), reduces them over the block and adds one fp64
+// (sum, sum of squares) pair per channel to acc[b][c] — the accumulation scheme of instnorm_acc_kernel, without reading
+// the tensor a second time.
+__global__ void __launch_bounds__(256) transpose_add_stats_kernel(float* __restrict__ x, const float* __restrict__ g, int F,
+                                                                  int C, int64_t ld, int64_t T, int fs,
+                                                                  double* __restrict__ acc) {
+  __shared__ float tile[32][33];
+  __shared__ float red[2][8][32];
+  const int64_t bt = blockIdx.z;
+  const int c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float s = 0.f, ss = 0.f;
+  for (int ft = 0; ft < fs; ++ft) {
+    const int f0 = (blockIdx.y * fs + ft) * 32;
+    if (f0 >= F) break;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k, f = f0 + tx;
+      tile[ty + 8 * k][tx] = (c < C && f < F) ? g[(bt * C + c) * F + f] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int f = f0 + ty + 8 * k, c = c0 + tx;
+      if (f < F && c < C) {
+        float* xp = x + (bt * F + f) * ld + c;
+        const float v = *xp + tile[tx][ty + 8 * k];
+        *xp = v;
+        s += v;
+        ss = fmaf(v, v, ss);
+      }
+    }
+    __syncthreads();
+  }
+  red[0][ty][tx] = s;
+  red[1][ty][tx] = ss;
+  __syncthreads();
+  if (ty == 0 && c0 + tx < C) {
+#pragma unroll
+    for (int l = 1; l < 8; ++l) { s += red[0][l][tx]; ss += red[1][l][tx]; }
+    const int64_t b = bt / T;
+    atomicAdd(&acc[(b * C + c0 + tx) * 2], (double)s);
+    atomicAdd(&acc[(b * C + c0 + tx) * 2 + 1], (double)ss);
+  }
+}
+
 // spec (sesa_stft layout 0) [bt][f_full][c2] -> mix[bt][f'][c2*k + kk], f_full = kk*Fs + f'   (cac2cws, :191-196)
 __global__ void mdx_pack_kernel(const float* __restrict__ spec, int64_t BT, int F_full, int Fs, int k, int c2,
                                 float* __restrict__ mix) {
@@ -483,6 +531,25 @@ extern "C" int sesa_transpose_add(float* x, const float* g, int64_t bt, int F, i
   SESA_CHECK_ARG(bt <= 65535, "sesa_transpose_add: too many (b, t) slices for one launch");
   dim3 grid((channels + 31) / 32, (F + 31) / 32, (unsigned)bt);
   transpose_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, g, F, channels, ld);
+  SESA_LAUNCH_CHECK();
+  return SESA_OK;
+}
+
+extern "C" int sesa_transpose_add_stats(float* x, const float* g, int batch, int64_t frames, int F, int channels, int64_t ld,
+                                        double* scratch, float* stats, float eps, void* stream) {
+  const int64_t bt = (int64_t)batch * frames;
+  if (bt <= 0) return SESA_OK;
+  SESA_CHECK_ARG(bt <= 65535, "sesa_transpose_add_stats: too many (b, t) slices for one launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  SESA_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)batch * channels, st));
+  const int ftiles = (F + 31) / 32;
+  const int fs = ftiles >= 8 ? 8 : ftiles;       // frequency tiles per block: 8x fewer atomics than one tile per block
+  dim3 grid((channels + 31) / 32, (ftiles + fs - 1) / fs, (unsigned)bt);
+  transpose_add_stats_kernel<<<grid, 256, 0, st>>>(x, g, F, channels, ld, frames, fs, scratch);
+  SESA_LAUNCH_CHECK();
+  const int n = batch * channels;
+  instnorm_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(scratch, n, 1.0 / ((double)frames * F), eps,
+                                                            reinterpret_cast<float2*>(stats));
   SESA_LAUNCH_CHECK();
   return SESA_OK;
 }

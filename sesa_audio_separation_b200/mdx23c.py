@@ -182,16 +182,19 @@ class TFC_TDF_net(KernelModule):
         stats_scratch = torch.zeros(2 * B * 2048, device=dev, dtype=torch.float64)
         keep.append(stats_scratch)
 
-        def norm_planes(x, coff, C, stats_geo, split_geo, gamma, beta, out):
+        def norm_planes(x, coff, C, stats_geo, split_geo, gamma, beta, out, st=None):
             """InstanceNorm statistics per (b, c), then norm + affine + act + bf16 split into `out` planes.
-            stats_geo = (layout, n1, n2, ld) of sesa_instnorm_stats; split_geo = (mode, n1, n2, ld) of sesa_norm_act_split."""
-            st = buf(B, C, 2)
+            stats_geo = (layout, n1, n2, ld) of sesa_instnorm_stats; split_geo = (mode, n1, n2, ld) of sesa_norm_act_split.
+            ``st``: statistics already produced by the kernel that wrote x (no separate pass)."""
+            have = st is not None
+            st = st if have else buf(B, C, 2)
             xp = x.data_ptr() + 4 * coff
             (sl, sn1, sn2, sld), (mode, n1, n2, ld) = stats_geo, split_geo
 
             def run():
-                call('sesa_instnorm_stats', ctypes.c_void_p(xp), sl, B, sn1, C, sn2, sld, _ptr(stats_scratch), _ptr(st),
-                     1e-5, _stream())
+                if not have:
+                    call('sesa_instnorm_stats', ctypes.c_void_p(xp), sl, B, sn1, C, sn2, sld, _ptr(stats_scratch), _ptr(st),
+                         1e-5, _stream())
                 call('sesa_norm_act_split', ctypes.c_void_p(xp), mode, B, n1, C, n2, ld, _ptr(st), _ptr(gamma), _ptr(beta),
                      self.act, _ptr(out), out.shape[-1], out.stride(0), _stream())
             steps.append(run)
@@ -204,8 +207,10 @@ class TFC_TDF_net(KernelModule):
                         K=len(taps) * _r64(cin), C=(cptr, ldc),
                         conv=dict(cin=cin, B=B, T=Tt, F=Ff, inT=inT, inF=inF, stride=stride, taps=taps))
 
-        def tfc_tdf(prefix, x, x_ld, x_off, in_c, c, Tt, Ff, out, out_ld, out_off):
-            """One TFC_TDF module (:100-138); x: (tensor, ld, channel offset); writes `out` likewise."""
+        def tfc_tdf(prefix, x, x_ld, x_off, in_c, c, Tt, Ff, out, out_ld, out_off, x_raw, out_raw=None):
+            """One TFC_TDF module (:100-138); x: (tensor, ld, channel offset); writes `out` likewise.  ``x_raw``: bf16 planes
+            of the raw input (A operand of the first shortcut conv), written by whichever GEMM produced x; ``out_raw``
+            (planes tensor, column offset) asks the module's last GEMM to leave the raw planes of ITS output there."""
             M = B * Tt * Ff
             J = Ff // self.bn
             for i in range(self.l):
@@ -213,13 +218,11 @@ class TFC_TDF_net(KernelModule):
                 last = i == self.l - 1
                 y, y_ld, y_off = (out, out_ld, out_off) if last else (buf(M, c), c, 0)
                 yptr = y.data_ptr() + 4 * y_off
+                # raw planes of y for its consumer's shortcut conv come out of the tfc2 epilogue below (no separate pass)
+                y_raw = (planes(M, c), 0) if not last else out_raw
                 # shortcut: 1x1 conv of the raw input -> y
-                xr = planes(M, in_c)
-                xptr = x.data_ptr() + 4 * x_off
-                steps.append(lambda xptr=xptr, xr=xr, ld=x_ld, cc=in_c: call(
-                    'sesa_norm_act_split', ctypes.c_void_p(xptr), 0, B, Tt * Ff, cc, 1, ld, None, None, None, 0, _ptr(xr),
-                    xr.shape[-1], xr.stride(0), _stream()))
-                gemm([dict(A=tc.planes_arg(xr), W=tc.planes_arg(prep[q + 'shortcut.weight']), M=M, N=c, K=in_c,
+                xr, xr_off = x_raw
+                gemm([dict(A=tc.planes_arg(xr, xr_off), W=tc.planes_arg(prep[q + 'shortcut.weight']), M=M, N=c, K=in_c,
                            C=(yptr, y_ld))], _ep())
                 # tfc1: norm -> act -> conv3x3 -> x1
                 xa = planes(M, in_c)
@@ -237,13 +240,19 @@ class TFC_TDF_net(KernelModule):
                 gout = buf(B * Tt * c, Ff)
                 gemm([dict(A=tc.planes_arg(tb), W=tc.planes_arg(prep[q + 'tdf.5.weight']), M=B * Tt * c, N=Ff, K=J,
                            C=(gout.data_ptr(), Ff))], _ep())
-                steps.append(lambda x1=x1, gout=gout, c=c: call('sesa_transpose_add', _ptr(x1), _ptr(gout), B * Tt, Ff, c, c,
-                                                                 _stream()))
+                # x1 += tdf(x1), with the statistics of the sum for tfc2's norm gathered in the same pass
+                st2 = buf(B, c, 2)
+                steps.append(lambda x1=x1, gout=gout, c=c, st2=st2: call(
+                    'sesa_transpose_add_stats', _ptr(x1), _ptr(gout), B, Tt, Ff, c, c, _ptr(stats_scratch), _ptr(st2), 1e-5,
+                    _stream()))
                 # tfc2: norm -> act -> conv3x3, + shortcut (already in y) through the residual epilogue
                 xb = planes(M, c)
-                norm_planes(x1, 0, c, *cl(Tt * Ff, c), prep[q + 'tfc2.0.weight'], prep[q + 'tfc2.0.bias'], xb)
-                gemm([conv_problem(xb, prep[q + 'tfc2.2.weight'], c, Tt, Ff, Tt, Ff, 1, TAPS3, c, yptr, y_ld)], _ep(residual=1))
-                x, x_ld, x_off, in_c = y, y_ld, y_off, c
+                norm_planes(x1, 0, c, *cl(Tt * Ff, c), prep[q + 'tfc2.0.weight'], prep[q + 'tfc2.0.bias'], xb, st=st2)
+                pr = conv_problem(xb, prep[q + 'tfc2.2.weight'], c, Tt, Ff, Tt, Ff, 1, TAPS3, c, yptr, y_ld)
+                if y_raw is not None:
+                    pr['P'] = tc.planes_arg(y_raw[0], y_raw[1])
+                gemm([pr], _ep(residual=1))
+                x, x_ld, x_off, in_c, x_raw = y, y_ld, y_off, c, y_raw
             return x, x_ld, x_off
 
         # ---- front end: STFT -> sub-band channels (cac2cws) -> first_conv
@@ -257,41 +266,47 @@ class TFC_TDF_net(KernelModule):
         steps.append(lambda: call('sesa_mdx_pack', _ptr(spec), B * T, Ffull, self.fs, self.k, C2, _ptr(mix), _stream()))
         steps.append(lambda: call('sesa_norm_act_split', _ptr(mix), 0, B, T * self.fs, self.dim_c, 1, self.dim_c, None, None,
                                   None, 0, _ptr(mixp), mixp.shape[-1], mixp.stride(0), _stream()))
+        x_raw = (planes(M0, c), 0)
         gemm([dict(A=tc.planes_arg(mixp), W=tc.planes_arg(prep['first_conv.weight']), M=M0, N=c, K=self.dim_c,
-                   C=(first.data_ptr(), c))], _ep())
+                   C=(first.data_ptr(), c), P=tc.planes_arg(x_raw[0]))], _ep())
         # ---- encoder
         x, x_ld, x_off = first, c, 0
         Tt, Ff = T, self.fs
         skips = []
         for i in range(self.n):
             cat = buf(B * Tt * Ff, 2 * c)      # decoder concat buffer: [upscaled | encoder output]
-            x, x_ld, x_off = tfc_tdf(f'encoder_blocks.{i}.tfc_tdf.', x, x_ld, x_off, c, c, Tt, Ff, cat, 2 * c, c)
-            skips.append((cat, c, Tt, Ff))
+            catp = planes(B * Tt * Ff, 2 * c)  # its raw planes: both halves are written by the GEMMs that produce them
+            x, x_ld, x_off = tfc_tdf(f'encoder_blocks.{i}.tfc_tdf.', x, x_ld, x_off, c, c, Tt, Ff, cat, 2 * c, c, x_raw,
+                                     out_raw=(catp, c))
+            skips.append((cat, catp, c, Tt, Ff))
             p = f'encoder_blocks.{i}.downscale.conv.'
             xa = planes(B * Tt * Ff, c)
             norm_planes(x, x_off, c, *cl(Tt * Ff, x_ld), prep[p + '0.weight'], prep[p + '0.bias'], xa)
             nxt = buf(B * (Tt // 2) * (Ff // 2), c + self.g)
-            gemm([conv_problem(xa, prep[p + '2.weight'], c, Tt // 2, Ff // 2, Tt, Ff, 2, TAPS2, c + self.g, nxt.data_ptr(),
-                               c + self.g)], _ep())
+            x_raw = (planes(B * (Tt // 2) * (Ff // 2), c + self.g), 0)
+            pr = conv_problem(xa, prep[p + '2.weight'], c, Tt // 2, Ff // 2, Tt, Ff, 2, TAPS2, c + self.g, nxt.data_ptr(),
+                              c + self.g)
+            pr['P'] = tc.planes_arg(x_raw[0])
+            gemm([pr], _ep())
             x, x_ld, x_off = nxt, c + self.g, 0
             Tt, Ff, c = Tt // 2, Ff // 2, c + self.g
         bott = buf(B * Tt * Ff, c)
-        x, x_ld, x_off = tfc_tdf('bottleneck_block.', x, x_ld, x_off, c, c, Tt, Ff, bott, c, 0)
+        x, x_ld, x_off = tfc_tdf('bottleneck_block.', x, x_ld, x_off, c, c, Tt, Ff, bott, c, 0, x_raw)
         # ---- decoder
         for i in range(self.n):
             p = f'decoder_blocks.{i}.upscale.conv.'
-            cat, cs, Ts, Fs_ = skips.pop()
+            cat, catp, cs, Ts, Fs_ = skips.pop()
             xa = planes(B * Tt * Ff, c)
             norm_planes(x, x_off, c, *cl(Tt * Ff, x_ld), prep[p + '0.weight'], prep[p + '0.bias'], xa)
             probs = []
             for ti, (kh, kw) in enumerate(TAPS2):
                 probs.append(dict(A=tc.planes_arg(xa), W=tc.planes_arg(prep[p + '2.weight'][ti]), M=B * Tt * Ff, N=c - self.g,
-                                  K=c, C=(cat.data_ptr(), 2 * cs), row_map=(Ff, kh, kw)))
+                                  K=c, C=(cat.data_ptr(), 2 * cs), P=tc.planes_arg(catp), row_map=(Ff, kh, kw)))
             gemm(probs, _ep())
             Tt, Ff, c = Tt * 2, Ff * 2, c - self.g
             assert (cs, Ts, Fs_) == (c, Tt, Ff)
             dec = buf(B * Tt * Ff, c)
-            x, x_ld, x_off = tfc_tdf(f'decoder_blocks.{i}.tfc_tdf.', cat, 2 * c, 0, 2 * c, c, Tt, Ff, dec, c, 0)
+            x, x_ld, x_off = tfc_tdf(f'decoder_blocks.{i}.tfc_tdf.', cat, 2 * c, 0, 2 * c, c, Tt, Ff, dec, c, 0, (catp, 0))
         # ---- head: x * first_conv_out, cat(mix, x), final_conv (1x1 -> act -> 1x1)
         fin = planes(M0, self.dim_c + c)
         steps.append(lambda x=x, ld=x_ld: call('sesa_mdx_final_concat', _ptr(mix), self.dim_c, _ptr(x), ld, _ptr(first), c, c, M0,

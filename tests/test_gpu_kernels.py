@@ -760,3 +760,29 @@ def test_rmsnorm_planes_equals_the_two_kernel_sequence(lib, dim, out_planes):
     assert torch.equal(pa[:out_planes], pb[:out_planes])
     ref = torch.nn.functional.normalize(x, dim=-1) * dim ** 0.5 * gamma
     assert max_rel(ref.cpu().numpy(), b.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize('B,T,F,C', [(2, 8, 64, 96), (1, 16, 256, 128), (2, 4, 40, 72)])
+def test_transpose_add_stats_equals_the_two_pass_sequence(lib, B, T, F, C):
+    """x += tdf(x)^T with the InstanceNorm statistics of the sum gathered in the same pass: x is bit-identical to
+    sesa_transpose_add, the (mean, rstd) pairs agree with sesa_instnorm_stats over the updated tensor and with torch."""
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(B * 1000 + F)
+    x = torch.randn(B * T * F, C, device=dev, generator=g) * 2 + 0.3
+    gt = torch.randn(B * T * C, F, device=dev, generator=g)
+    a = x.clone()
+    lib.call('sesa_transpose_add', P(a), P(gt), B * T, F, C, C, S())
+    scratch = torch.zeros(2 * B * C, device=dev, dtype=torch.float64)
+    sa = torch.empty(B, C, 2, device=dev)
+    lib.call('sesa_instnorm_stats', P(a), 0, B, T * F, C, 1, C, P(scratch), P(sa), 1e-5, S())
+    b = x.clone()
+    sb = torch.empty(B, C, 2, device=dev)
+    lib.call('sesa_transpose_add_stats', P(b), P(gt), B, T, F, C, C, P(scratch), P(sb), 1e-5, S())
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert torch.allclose(sa, sb, rtol=2e-6, atol=1e-7)
+    ref = a.view(B, T * F, C).double()
+    mean = ref.mean(1)
+    rstd = 1.0 / torch.sqrt(ref.var(1, unbiased=False) + 1e-5)
+    assert torch.allclose(sb[..., 0].double(), mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(sb[..., 1].double(), rstd, rtol=1e-5)
