@@ -97,6 +97,25 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * fmaf(0.5f, ef, 0.5f);
 }
 
+// tanh (MaskEstimator MLPs, bs_roformer.py:271) in ~15 branch-free instructions: |x| < 0.5 -> x + x^3 P(x^2) (degree-3
+// minimax fit, max relative error 7.4e-8 evaluated in fp32); otherwise 1 - 2 / (2^(2 log2(e) |x|) + 1) with ex2.approx and
+// rcp.approx (max relative error 1.7e-7).  tanhf() costs about twice as much and made the K = 384 mask layer of the
+// 4-stem Mel model epilogue-bound (41 % tensor-pipe activity, profiles/r2_mel_launches.md).
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float a = fabsf(x);
+  const float u = x * x;
+  float p = 0.017544856294989586f;
+  p = fmaf(p, u, -0.05318477749824524f);
+  p = fmaf(p, u, 0.1332780420780182f);
+  p = fmaf(p, u, -0.33333221077919006f);
+  const float small = fmaf(x * u, p, x);
+  const float e = tc::ex2_approx(a * 2.8853900817779268f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  const float big = copysignf(fmaf(-2.0f, r, 1.0f), x);
+  return a < 0.5f ? small : big;
+}
+
 // The same polynomial over 16 values, written breadth-first (each Horner step over all 16 before the next) so that the
 // epilogue warps always have independent instructions to issue: two warps per scheduler cannot hide a serial chain.
 __device__ __forceinline__ void gelu_fast16(float4 (&o)[4]) {
@@ -168,7 +187,19 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
   const int cta_rank = CG == 2 ? (int)tc::cluster_ctarank() : 0;
   const bool leader = cta_rank == 0;
   const int unit = blockIdx.x / CG;         // CTA (pair) index: the tile scheduler's granularity
-  const int n_units = gridDim.x / CG;
+  int n_units = gridDim.x / CG;
+  // Static round-robin (unit u takes tiles u, u + n_units, ...) resonates with the column-block count when the two share
+  // a factor: with N = 384 (256 + 128 columns) and 74 units, every odd unit would only ever get the half-width tiles and
+  // sit idle for half of the launch.  When a single problem has a ragged last column block, the stride is reduced until it
+  // is coprime with the column-block count (one or two units go without work: 1-3 % of the machine instead of 25 %).
+  if (n_groups == 1) {
+    const int nbk = groups[0].n_blocks;
+    if (nbk > 1 && groups[0].N % BN != 0) {
+      auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+      while (n_units > 1 && gcd(n_units, nbk) != 1) --n_units;
+    }
+  }
+  const int first_tile = unit < n_units ? unit : total_tiles;   // units beyond the stride own no tiles
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -220,7 +251,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     if (tc::elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = unit; tile < total_tiles; tile += n_units) {
+      for (int tile = first_tile; tile < total_tiles; tile += n_units) {
         const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
         const int t = tile - g->tile_begin;
         const int mb = (t / g->n_blocks) * CG + cta_rank, nb = t % g->n_blocks;
@@ -278,7 +309,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = unit; tile < total_tiles; tile += n_units) {
+      for (int tile = first_tile; tile < total_tiles; tile += n_units) {
         const TcGroup* g = &groups[find_group(tile_end, n_groups, tile)];
         const int kbs = g->k_blocks;
         // the last column block of a problem only multiplies the columns that exist (N granularity 16; 32 for a pair)
@@ -338,7 +369,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
     const int rb = lane >> 2;        // phase B: row (within each group of 8) handled by this lane
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = unit; tile < total_tiles; tile += n_units) {
+    for (int tile = first_tile; tile < total_tiles; tile += n_units) {
       const int gi = n_groups == 1 ? 0 : find_group(tile_end, n_groups, tile);
       const TcGroup* g = n_groups == 1 ? g_local : &groups[gi];
       const int t = tile - g->tile_begin;
@@ -420,7 +451,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
           if (FLAVOR == F_GELU) gelu_fast16(o);
           if (FLAVOR == F_TANH) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { o[k].x = tanhf(o[k].x); o[k].y = tanhf(o[k].y); o[k].z = tanhf(o[k].z); o[k].w = tanhf(o[k].w); }
+            for (int k = 0; k < 4; ++k) { o[k].x = tanh_fast(o[k].x); o[k].y = tanh_fast(o[k].y); o[k].z = tanh_fast(o[k].z); o[k].w = tanh_fast(o[k].w); }
           }
           if (do_rot) {
 #pragma unroll
@@ -612,7 +643,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
           } else if (act == SESA_ACT_TANH) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-              o[it].x = tanhf(o[it].x); o[it].y = tanhf(o[it].y); o[it].z = tanhf(o[it].z); o[it].w = tanhf(o[it].w);
+              o[it].x = tanh_fast(o[it].x); o[it].y = tanh_fast(o[it].y); o[it].z = tanh_fast(o[it].z); o[it].w = tanh_fast(o[it].w);
             }
           } else if (act == SESA_ACT_SIGMOID) {
 #pragma unroll
@@ -667,7 +698,7 @@ gemm_tc_kernel(const TcGroup* __restrict__ groups, int n_groups, int total_tiles
             if (act == SESA_ACT_GELU) {
               o.x = gelu_fast(o.x); o.y = gelu_fast(o.y); o.z = gelu_fast(o.z); o.w = gelu_fast(o.w);
             } else if (act == SESA_ACT_TANH) {
-              o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
+              o.x = tanh_fast(o.x); o.y = tanh_fast(o.y); o.z = tanh_fast(o.z); o.w = tanh_fast(o.w);
             } else if (act == SESA_ACT_SIGMOID) {
               o.x = 1.0f / (1.0f + expf(-o.x)); o.y = 1.0f / (1.0f + expf(-o.y));
               o.z = 1.0f / (1.0f + expf(-o.z)); o.w = 1.0f / (1.0f + expf(-o.w));
