@@ -220,17 +220,6 @@ int sesa_overlap_add(const float* chunk_out, const int64_t* starts, const int64_
                      int nstems, int channels, int64_t padded_len, int64_t crop, int64_t out_len,
                      float* result, float* counter, void* stream);
 
-/* The same overlap-add restricted to this rank's chunks [k_lo, k_hi) (chunk_out holds only those) and to padded
- * positions [p_begin, p_end): the chunk-range sharding of SURVEY 8e.  init (optional, [nstems*channels][init_len])
- * seeds positions [init_p0, init_p0+init_len) with the previous rank's raw sums (keeps utils.py:439-442's ascending
- * addition order).  mode 0: out = result[n][c][out_len] (divided by the GLOBAL counter, cropped); mode 1: out =
- * raw sums [nstems*channels][p_end-p_begin] to hand to the next rank. */
-int sesa_overlap_add_range(const float* chunk_out, const int64_t* starts, const int64_t* lens, const int32_t* kinds,
-                           int n_chunks, int k_lo, int k_hi, int64_t step, int64_t chunk_size, int fade,
-                           const float* window, int nstems, int channels, int64_t p_begin, int64_t p_end,
-                           const float* init, int64_t init_p0, int64_t init_len, int mode, int64_t crop,
-                           int64_t out_len, float* out, void* stream);
-
 /* RMSNorm at the end of a Mel-Band Transformer (mel_band_roformer.py:218,226) fused with the operand preparation of the
  * next GEMM: x[rows][dim] <- x / max(||x||, 1e-12) * sqrt(dim) * gamma in place, planes <- bf16 hi/lo of the new rows,
  * ss_out[row][ss_slots] <- (sum of squares of the new row, 0, ...).  Bit-identical to sesa_rmsnorm followed by

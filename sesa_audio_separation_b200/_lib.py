@@ -85,9 +85,6 @@ _SIGS = {
     'sesa_mdx_final_concat': (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_void_p,
                                       c_int64, c_int64, c_void_p]),
     'sesa_mdx_unpack': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    'sesa_overlap_add_range': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64,
-                                       c_int, c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64,
-                                       c_int, c_int64, c_int64, c_void_p, c_void_p]),
     'sesa_rmsnorm_planes': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p]),
     'sesa_overlap_accumulate': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int,
                                         c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_int64, c_int64, c_int64,
@@ -133,7 +130,7 @@ LAUNCHES = 0
 _profile = None   # dict: class -> [ (start_event, end_event), ... ] when enabled
 _CLASS = {'sesa_gemm_simt': 'gemm_simt', 'sesa_gemm_tc': 'gemm_tc', 'sesa_prep_rows': 'prep_rows', 'sesa_rmsnorm_planes': 'prep_rows', 'sesa_rmsnorm': 'prep_rows', 'sesa_add_inplace': 'prep_rows', 'sesa_band_prep': 'prep_rows', 'sesa_instnorm_stats': 'norm', 'sesa_norm_act_split': 'norm', 'sesa_transpose_add': 'norm', 'sesa_transpose_add_stats': 'norm', 'sesa_attention_simt': 'attention',
           'sesa_attention_tc': 'attention', 'sesa_stft': 'stft', 'sesa_mask_istft': 'mask_istft',
-          'sesa_overlap_add': 'overlap_add', 'sesa_overlap_add_range': 'overlap_add', 'sesa_overlap_accumulate': 'overlap_add', 'sesa_pad_reflect_slice': 'framing',
+          'sesa_overlap_add': 'overlap_add', 'sesa_overlap_accumulate': 'overlap_add', 'sesa_pad_reflect_slice': 'framing',
           'sesa_tta_variants': 'tta', 'sesa_tta_combine': 'tta', 'sesa_ensemble_wave': 'ensemble', 'sesa_frame_chunks': 'framing', 'sesa_pad_reflect': 'framing'}
 
 

@@ -1,6 +1,6 @@
 """Audio file I/O for the CLI drivers (reference: librosa.load at inference_pytorch.py:213, sf.write at :272).
 
-``soundfile`` / ``librosa`` are used when importable (they are the reference's own I/O and give FLAC); otherwise a
+``librosa`` / ``soundfile`` are used when importable (they are the reference's own I/O: same resampler, FLAC); otherwise a
 self-contained WAV path is used: scipy.io.wavfile for reading (PCM 8/16/24/32 and float), polyphase resampling to the
 config sample rate, and an own RIFF writer for FLOAT / PCM_16 / PCM_24.  Host-side only; never on the timed path.
 """
@@ -12,6 +12,14 @@ import numpy as np
 
 def load_audio(path, sample_rate):
     """-> (mix float32 [channels, samples], sample_rate): the contract of librosa.load(path, sr=..., mono=False)."""
+    try:
+        # the reference's own call (inference_pytorch.py:213) whenever librosa is installed: identical decoding and the
+        # soxr resampler it uses when the file's rate differs from the config's
+        import librosa
+        mix, sr = librosa.load(path, sr=sample_rate, mono=False)
+        return np.ascontiguousarray(mix, dtype=np.float32), sr
+    except ImportError:
+        pass
     try:
         import soundfile as sf
         data, sr = sf.read(path, dtype='float32', always_2d=True)

@@ -372,68 +372,6 @@ extern "C" int sesa_overlap_add(const float* chunk_out, const int64_t* starts, c
 }
 
 
-// Chunk-range sharded overlap-add: the same gather as overlap_add_kernel restricted to the chunks
-// [k_lo, k_hi) held by this rank and to padded positions [p_begin, p_end).  `init` seeds the accumulator with the
-// previous rank's partial sums (its chunks precede ours, so seeding keeps the reference's ascending-chunk addition
-// order bit-exact).  mode 0: result = acc / counter (counter from the GLOBAL schedule), cropped; mode 1: raw sums.
-__global__ void overlap_add_range_kernel(const float* __restrict__ y, const int64_t* __restrict__ starts,
-                                         const int64_t* __restrict__ lens, const int32_t* __restrict__ kinds,
-                                         int n_chunks, int k_lo_own, int k_hi_own, int64_t step, int64_t L, int fade,
-                                         const float* __restrict__ window, int nc, int64_t p_begin, int64_t p_end,
-                                         const float* __restrict__ init, int64_t init_p0, int64_t init_len,
-                                         int mode, int64_t crop, int64_t out_len, float* __restrict__ out) {
-  const int64_t p = p_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= p_end) return;
-  int64_t k_hi = p / step;
-  if (k_hi > n_chunks - 1) k_hi = n_chunks - 1;
-  int64_t k_lo = (p - L + step) / step;
-  if (p - L + 1 <= 0) k_lo = 0;
-  float cnt = 0.f;
-  if (mode == 0) {
-    for (int64_t k = k_lo; k <= k_hi; ++k) {
-      const int64_t o = p - starts[k];
-      if (o < 0 || o >= lens[k]) continue;
-      cnt = __fadd_rn(cnt, demix_window(window, o, L, fade, kinds[k]));
-    }
-    const int64_t io = p - crop;
-    if (io < 0 || io >= out_len) return;
-  }
-  const bool seeded = init != nullptr && p >= init_p0 && p < init_p0 + init_len;
-  for (int sc = 0; sc < nc; ++sc) {
-    float acc = seeded ? init[(int64_t)sc * init_len + (p - init_p0)] : 0.f;
-    for (int64_t k = k_lo > k_lo_own ? k_lo : k_lo_own; k <= k_hi && k < k_hi_own; ++k) {
-      const int64_t o = p - starts[k];
-      if (o < 0 || o >= lens[k]) continue;
-      const float w = demix_window(window, o, L, fade, kinds[k]);
-      acc = __fadd_rn(acc, __fmul_rn(y[((int64_t)(k - k_lo_own) * nc + sc) * L + o], w));
-    }
-    if (mode == 0) {
-      float r = acc / cnt;
-      if (r != r) r = 0.f;
-      out[(int64_t)sc * out_len + (p - crop)] = r;
-    } else {
-      out[(int64_t)sc * (p_end - p_begin) + (p - p_begin)] = acc;
-    }
-  }
-}
-
-extern "C" int sesa_overlap_add_range(const float* chunk_out, const int64_t* starts, const int64_t* lens,
-                                      const int32_t* kinds, int n_chunks, int k_lo, int k_hi, int64_t step,
-                                      int64_t chunk_size, int fade, const float* window, int nstems, int channels,
-                                      int64_t p_begin, int64_t p_end, const float* init, int64_t init_p0,
-                                      int64_t init_len, int mode, int64_t crop, int64_t out_len, float* out,
-                                      void* stream) {
-  SESA_CHECK_ARG(step > 0 && chunk_size >= step, "sesa_overlap_add_range: bad step %lld", (long long)step);
-  SESA_CHECK_ARG(0 <= k_lo && k_lo <= k_hi && k_hi <= n_chunks, "sesa_overlap_add_range: bad chunk range");
-  SESA_CHECK_ARG(mode == 0 || mode == 1, "sesa_overlap_add_range: mode must be 0 or 1");
-  if (p_end <= p_begin) return SESA_OK;
-  overlap_add_range_kernel<<<(unsigned)ceil_div64(p_end - p_begin, 256), 256, 0, (cudaStream_t)stream>>>(
-      chunk_out, starts, lens, kinds, n_chunks, k_lo, k_hi, step, chunk_size, fade, window, nstems * channels, p_begin,
-      p_end, init, init_p0, init_len, mode, crop, out_len, out);
-  SESA_LAUNCH_CHECK();
-  return SESA_OK;
-}
-
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                       float* __restrict__ y, int64_t rows, int dim, float scale) {
