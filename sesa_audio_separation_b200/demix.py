@@ -1,11 +1,14 @@
 """Chunked separation inference: the B200-native ``demix`` (reference: utils.py:330-477 and its
 copy inference_pytorch.py:55-186).
 
-What changes relative to the reference loop: the mix is uploaded ONCE, border padding, chunk framing,
-the model forward, the windowed overlap-add, the divide and the crop all run on the device, and the
-result comes back in ONE device->host copy (the reference does an H2D and a D2H + sync per chunk and
-accumulates on the CPU).  What does not change: the chunk schedule, pad modes, per-flush window rule
-and the ascending-order accumulation, which are reproduced bit-exactly (plan.py, sesa_overlap_add).
+What changes relative to the reference loop: the mix is uploaded ONCE; border padding, chunk framing, the model
+forward, the windowed overlap-add (streamed: every engine batch is folded into the running sums as soon as its
+forward is done), the divide and the crop all run on the device; finished regions of the result leave for page-locked
+host memory while later batches are still computing (the reference does an H2D and a D2H + sync per chunk and
+accumulates on the CPU).  What does not change: the chunk schedule, pad modes, per-flush window rule and the
+ascending-order accumulation, which are reproduced bit-exactly (plan.py, sesa_overlap_accumulate).  One track can also be
+sharded over several GPUs in contiguous chunk ranges (distributed.py), and the test-time-augmentation variants of a mix
+run as extra chunks of the same engine run.
 """
 import ctypes
 
