@@ -109,8 +109,13 @@ def _phase_remix(config, model, args, device, mix_orig, estimates, instruments):
 def run_folder(backend, args, config, device, model=None):
     start_time = time.time()
     mixture_paths = sorted(glob.glob(os.path.join(args.input_folder, '*.*')))
+    # under torchrun (one process per GPU) the files of the folder are sharded round-robin over the ranks: tracks are
+    # independent, so this needs no communication (BASELINE configs 4-5: "track-sharded across 8 x B200")
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    if world > 1:
+        mixture_paths = mixture_paths[rank::world]
     sample_rate = getattr(config.audio, 'sample_rate', 44100)
-    print(f"B200 backend | {len(mixture_paths)} files | SR: {sample_rate}")
+    print(f"B200 backend | {len(mixture_paths)} files | SR: {sample_rate}" + (f" | rank {rank}/{world}" if world > 1 else ""))
     instruments = prefer_target_instrument(config)[:]
     os.makedirs(args.store_dir, exist_ok=True)
     detailed_pbar = not args.disable_detailed_pbar
@@ -164,7 +169,10 @@ def proc_folder(argv=None):
     if args.force_cpu:
         raise _lib.SesaError('--force_cpu: the B200 engine has no CPU path')
     _lib.require_cuda()
-    device = f'cuda:{args.device_ids[0]}' if isinstance(args.device_ids, list) else f'cuda:{args.device_ids}'
+    if int(os.environ.get('WORLD_SIZE', 1)) > 1 and 'LOCAL_RANK' in os.environ:
+        device = f"cuda:{int(os.environ['LOCAL_RANK'])}"          # torchrun: one process per GPU
+    else:
+        device = f'cuda:{args.device_ids[0]}' if isinstance(args.device_ids, list) else f'cuda:{args.device_ids}'
     print(f"Using device: {device}")
     t0 = time.time()
     model, config = get_model_from_config(args.model_type, args.config_path)
