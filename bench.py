@@ -490,10 +490,19 @@ def main():
                                            'saturated_frac': v['gbs'] / hbm_peak, 'saturated_chunks_per_launch': 16})
             torch.cuda.empty_cache()
         if world == 1 and tc_mode and args.precision == 'fp32' and not args.no_configs:
-            line['configs'] = {name: sub_config(name, dev, tf_peak, hbm_peak) for name in ('c1_mdx23c', 'c3_mel4')}
+            line['configs'] = {}
+            for name in ('c1_mdx23c', 'c3_mel4'):
+                try:
+                    line['configs'][name] = sub_config(name, dev, tf_peak, hbm_peak)
+                except Exception as e:      # a sub-record must never cost the headline line
+                    line['configs'][name] = {'error': f'{type(e).__name__}: {e}'[:300]}
+                    torch.cuda.empty_cache()
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference(state_dict, args.seconds, 2, 1)
-            line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+            try:
+                cb = cpu_reference(state_dict, args.seconds, 2, 1)
+                line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+            except Exception as e:
+                line['cpu_baseline'] = {'error': f'{type(e).__name__}: {e}'[:300]}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
