@@ -422,7 +422,10 @@ def main():
 
     strong = None
     if world > 1 and not args.no_strong:
-        strong = strong_scaling(dev, rank, world, steps=max(2, min(args.steps, 5)), warmup=1)
+        try:
+            strong = strong_scaling(dev, rank, world, steps=max(2, min(args.steps, 5)), warmup=1)
+        except Exception as e:          # (a failure every rank hits alike: the weak-scaling line above still goes out)
+            strong = {'error': f'{type(e).__name__}: {e}'[:300]}
 
     if rank == 0:
         audio_s = args.seconds * world * args.steps
@@ -476,7 +479,11 @@ def main():
             # for 10-100 us kernels
             sys.path.insert(0, os.path.join(ROOT, 'tools'))
             import hbm_bench
-            iso = hbm_bench.measure(chunks=args.engine_batch, reps=5, seconds=args.seconds)
+            try:
+                iso = hbm_bench.measure(chunks=args.engine_batch, reps=5, seconds=args.seconds)
+            except Exception as e:
+                iso = {}
+                line['kernels']['isolated_error'] = f'{type(e).__name__}: {e}'[:300]
             for k, v in iso.items():
                 line['kernels'].setdefault(k, {'bound': 'hbm', 'peak': hbm_peak, 'unit': 'GB/s'})
                 line['kernels'][k].update({'isolated_us_per_launch': round(v['us'], 1), 'isolated_achieved': v['gbs'],
@@ -484,7 +491,11 @@ def main():
             torch.cuda.empty_cache()
             # and at a launch size that saturates the memory system (16 chunks per launch = 4x the product's engine batch):
             # separates what the KERNEL reaches from what a 10-70 us launch can reach at all
-            big = hbm_bench.measure(chunks=16, reps=5, seconds=args.seconds)
+            try:
+                big = hbm_bench.measure(chunks=16, reps=5, seconds=args.seconds)
+            except Exception as e:
+                big = {}
+                line['kernels']['saturated_error'] = f'{type(e).__name__}: {e}'[:300]
             for k, v in big.items():
                 line['kernels'][k].update({'saturated_us_per_launch': round(v['us'], 1), 'saturated_achieved': v['gbs'],
                                            'saturated_frac': v['gbs'] / hbm_peak, 'saturated_chunks_per_launch': 16})
