@@ -497,6 +497,7 @@ def main():
                 big = {}
                 line['kernels']['saturated_error'] = f'{type(e).__name__}: {e}'[:300]
             for k, v in big.items():
+                line['kernels'].setdefault(k, {'bound': 'hbm', 'peak': hbm_peak, 'unit': 'GB/s'})
                 line['kernels'][k].update({'saturated_us_per_launch': round(v['us'], 1), 'saturated_achieved': v['gbs'],
                                            'saturated_frac': v['gbs'] / hbm_peak, 'saturated_chunks_per_launch': 16})
             torch.cuda.empty_cache()
