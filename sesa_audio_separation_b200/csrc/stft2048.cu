@@ -33,14 +33,25 @@ __device__ __forceinline__ float2 cmulw(float2 a, float wr, float wi) {
   return INV ? make_float2(a.x * wr + a.y * wi, a.y * wr - a.x * wi) : make_float2(a.x * wr - a.y * wi, a.y * wr + a.x * wi);
 }
 
+// complex add / subtract as ONE packed fp32x2 instruction each (FADD2 / FFMA2 with a (-1, -1) multiplier: b * -1 is exact,
+// so a - b is rounded once, exactly like a scalar subtraction): the butterflies are what bounds these kernels (instruction
+// issue, not bytes), and two thirds of their arithmetic is complex additions
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+
 template <bool INV>
 __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
-  const float2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
-  const float2 j = INV ? make_float2(-bmd.y, bmd.x) : make_float2(bmd.y, -bmd.x);   // -/+ i (b - d)
-  a = cadd(apc, bpd);
-  b = cadd(amc, j);
-  c = csub(apc, bpd);
-  d = csub(amc, j);
+  const float2 apc = padd(a, c), amc = psub(a, c), bpd = padd(b, d), bmd = psub(b, d);
+  a = padd(apc, bpd);
+  c = psub(apc, bpd);
+  // b, d = amc +/- (-/+ i) bmd: component-swapped operands, cheaper as four scalar additions than as packed ones
+  if (INV) {
+    b = make_float2(amc.x - bmd.y, amc.y + bmd.x);
+    d = make_float2(amc.x + bmd.y, amc.y - bmd.x);
+  } else {
+    b = make_float2(amc.x + bmd.y, amc.y - bmd.x);
+    d = make_float2(amc.x - bmd.y, amc.y + bmd.x);
+  }
 }
 
 // 16-point DFT in registers.  In: v[m] natural order.  Out: X[k] is left in v[4 * (k & 3) + (k >> 2)].
@@ -75,8 +86,8 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
 #pragma unroll
   for (int k0 = 0; k0 < 4; ++k0) {
     const float2 e = v[2 * k0], o = v[2 * k0 + 1];
-    v[2 * k0] = cadd(e, o);
-    v[2 * k0 + 1] = csub(e, o);
+    v[2 * k0] = padd(e, o);
+    v[2 * k0 + 1] = psub(e, o);
   }
 }
 
